@@ -1,0 +1,298 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run once in the build container (the upstream checkout is read-only at
+``/root/reference`` and does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What it does
+------------
+1. imports the reference straight from ``/root/reference/src`` (nothing is copied);
+   three tiny stub modules stand in for packages that are not installed
+   (``bmipy`` -- only the ``Bmi`` base class is needed; ``timezonefinder`` -- the
+   polygon lookup is replaced by a fixed IANA zone, the DST arithmetic stays the
+   reference's own ``zoneinfo`` code; ``pyprojroot``) and a fake ``_version`` module
+   replaces the file hatch-vcs would generate;
+2. drives one reference instance per catchment through every case below, dumping every
+   intermediate of ``update()`` after each step;
+3. runs ``oracle/np_ref.py`` on the same inputs and REQUIRES bit-equality of every
+   dumped quantity (this is the gate that pins the oracle);
+4. writes ``*.npz`` fixtures holding inputs + the reference's outputs.
+
+Cases
+-----
+``sample265``   the reference's own integration test (tests/integration_test.py:67-153)
+``cats288``     the four shipped catchments (config/cat-*.yaml statics) x 288 sample rows
+``const``       run_topoflow_glacier_const.py:64-65 forcing override (RAINRATE=3, T2D=283.15)
+``allconst``    fully constant forcing + thin snow: snow -> ice hand-over
+``nosnow``      tests/integration_test.py:192-243
+``year4``       4 catchments x 8760 synthetic hourly steps across both 2012/13 DST switches
+``rand64``      64 random cells x 48 steps (wide parameter coverage incl. bare ground)
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REF = Path("/root/reference")
+os.environ["NGEN_EWTS_LOGGING"] = "DISABLED"
+
+DUMP = ["p0", "P_rain", "P_snow", "e_sat_air", "e_air", "RH", "T_dew", "T_surf", "e_sat_surf", "Ri", "Dn", "Dh",
+        "Qh", "W_p", "e_surf", "Qe", "TSN_offset", "albedo", "n", "Qn_SW", "em_air", "Qn_LW", "Q_sum", "SM", "IM",
+        "M_total", "h_swe", "h_iwe", "h_snow", "h_ice", "Eccs", "Ecci", "vol_P", "vol_PR", "vol_PS", "vol_SM",
+        "vol_IM", "P_max"]
+STATIC_KEYS = ["da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow"]
+
+
+def install_reference(tzname="America/Los_Angeles"):
+    bm = types.ModuleType("bmipy")
+    bm.Bmi = type("Bmi", (), {})
+    sys.modules["bmipy"] = bm
+    tzf = types.ModuleType("timezonefinder")
+
+    class TimezoneFinder:
+        def timezone_at(self, lat=None, lng=None):
+            return tzname
+
+        certain_timezone_at = timezone_at
+
+    tzf.TimezoneFinder = TimezoneFinder
+    sys.modules["timezonefinder"] = tzf
+    pp = types.ModuleType("pyprojroot")
+    pp.here = lambda: REF
+    sys.modules["pyprojroot"] = pp
+    ver = types.ModuleType("topoflow_glacier._version")
+    ver.__version__ = "0+reference"
+    sys.modules["topoflow_glacier._version"] = ver
+    sys.path.insert(0, str(REF / "src"))
+    # make sure the repo's own drop-in package of the same name is not picked up
+    sys.path[:] = [p for p in sys.path if Path(p or ".").resolve() != REPO]
+    import topoflow_glacier  # noqa: F401
+
+    assert str(REF) in topoflow_glacier.__file__, topoflow_glacier.__file__
+    return topoflow_glacier.BmiTopoflowGlacier
+
+
+def base_config(**over):
+    cfg = {"site_prefix": "cat-3062920", "forcing_file": "none.csv", "dt": 1, "start_time": "2013032000",
+           "end_time": "2013033100", "da": 11.418749923500716, "slope": 88.582729, "aspect": 242.8644693769529,
+           "lon": -121.81418, "lat": 46.81953220, "elev": 2446.3922737596167, "h_active_layer": 0.125,
+           "h0_snow": 5.0, "h0_ice": 2.0, "h0_swe": 0.25, "h0_iwe": 1.834, "T_rain_snow": 0.0}
+    cfg.update(over)
+    return cfg
+
+
+def shipped_configs():
+    import yaml
+
+    out = []
+    for name in ("cat-3062784", "cat-3062920", "cat-3062924", "cat-3062927"):
+        c = yaml.safe_load(open(REF / "config" / f"{name}.yaml"))
+        c["start_time"], c["end_time"] = str(c["start_time"]), str(c["end_time"])  # 3 yamls hold ints
+        out.append(c)
+    return out
+
+
+def sample_forcing(nrows=None):
+    """The driver-side unit conversions of examples/run_topoflow_glacier.py:40-73 -> [T, 5]."""
+    import pandas as pd
+
+    df = pd.read_csv(REF / "tests/data/sample-cat-3062920.csv")
+    if nrows:
+        df = df.iloc[:nrows]
+    P = df["RAINRATE"].values * 10 ** (-3)
+    T = -273.15 + df["T2D"].values
+    ws = (((df["U2D"]) ** 2 + (df["V2D"]) ** 2) ** 0.5).values
+    return np.stack([P, T, df["PSFC"].values, df["Q2D"].values, ws], axis=1)
+
+
+def run_reference(Bmi, cfgs, forcing, tmp):
+    """forcing [T, 5, N]; returns {name: [T, N]} of reference intermediates."""
+    import yaml
+
+    T, _, N = forcing.shape
+    out = {k: np.empty((T, N)) for k in DUMP}
+    for i, cfg in enumerate(cfgs):
+        p = tmp / f"cfg_{i}.yaml"
+        yaml.dump(cfg, open(p, "w"))
+        m = Bmi()
+        m.initialize(str(p))
+        for t in range(T):
+            f = forcing[t, :, i]
+            m.set_value("atmosphere_water__liquid_equivalent_precipitation_rate", np.array([f[0]]))
+            m.set_value("land_surface_air__temperature", np.array([f[1]]))
+            m.set_value("land_surface_air__pressure", np.array([f[2]]))
+            m.set_value("atmosphere_air_water~vapor__relative_saturation", np.array([f[3]]))
+            m.set_value("wind_speed_UV", np.array([f[4]]))
+            m.update()
+            for k in DUMP:
+                out[k][t, i] = np.asarray(getattr(m, k), dtype=np.float64).ravel()[0]
+    return out
+
+
+def run_oracle(cfgs, forcing, tz="America/Los_Angeles"):
+    sys.path.insert(0, str(REPO))
+    from oracle.np_ref import CellStatics, Constants, OracleModel
+
+    cells = CellStatics.from_configs(cfgs, tz=tz)
+    model = OracleModel(cells, Constants.from_mapping(cfgs[0]), start_time=cfgs[0]["start_time"], strict_pow=True)
+    T = forcing.shape[0]
+    out = {k: np.empty((T, cells.n)) for k in DUMP}
+    for t in range(T):
+        d = model.step(*forcing[t])
+        for k in DUMP:
+            out[k][t] = d[k] if k in d else getattr(model, k)
+    return out
+
+
+def synthetic_year(n_steps=8760, seed=20130320):
+    """SURVEY 8(d) cfg-3 generator; one met series shared by the four catchments."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    hours = np.arange(n_steps)
+    doy = (274 + hours // 24) % 365  # water year starts 1 Oct
+    hod = hours % 24
+    T2D = 273.15 + 2 + 9 * np.sin(2 * np.pi * (doy - 105) / 365) + 4 * np.sin(2 * np.pi * (hod - 15) / 24) \
+        + rng.normal(0, 2, n_steps)
+    PSFC = 88900 + rng.normal(0, 400, n_steps)
+    Tc = T2D - 273.15
+    esat = 611.0 * np.exp(17.3 * Tc / (Tc + 237.3))
+    qsat = 0.622 * esat / (PSFC - 0.378 * esat)
+    Q2D = np.clip(0.8 * qsat * rng.uniform(0.5, 1.0, n_steps), 5e-4, 0.012)
+    U, V = rng.normal(0, 3, n_steps), rng.normal(0, 3, n_steps)
+    rain = np.where(rng.uniform(size=n_steps) < 0.12, rng.exponential(0.5, n_steps), 0.0)  # mm/h
+    return np.stack([rain * 10 ** (-3), -273.15 + T2D, PSFC, Q2D, (U**2 + V**2) ** 0.5], axis=1)
+
+
+def random_cells(n=64, seed=4096):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cfgs = []
+    for i in range(n):
+        glacier = rng.uniform() < 0.4
+        snow = rng.uniform() < 0.7
+        swe = rng.uniform(0, 1.5) if snow else 0.0
+        iwe = rng.uniform(0, 60) if glacier else 0.0
+        if i % 16 == 0:
+            swe = rng.uniform(0, 0.002)  # melts out inside the window -> exercises the snow->ice switch
+        cfgs.append(base_config(
+            lat=rng.uniform(46.5, 47.1), lon=rng.uniform(-122.1, -121.4), elev=rng.uniform(1200, 4300),
+            slope=rng.uniform(0, 120), aspect=rng.uniform(0, 360), da=9e-4, h0_swe=swe, h0_snow=swe * 20.0,
+            h0_iwe=iwe, h0_ice=iwe * (1000.0 / 917.0), T_rain_snow=float(rng.choice([0.0, 1.0])),
+            start_time="2013010100"))
+    return cfgs
+
+
+def compare(ref, ora, name):
+    bad = []
+    for k in DUMP:
+        a, b = ref[k], ora[k]
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        if not same.all():
+            idx = np.argwhere(~same)[0]
+            rel = np.nanmax(np.abs(a - b) / np.maximum(np.abs(a), 1e-300))
+            bad.append(f"{k}: {np.count_nonzero(~same)}/{same.size} differ, first at {tuple(idx)}, max rel {rel:.3e}")
+    if bad:
+        raise SystemExit(f"[{name}] ORACLE != REFERENCE\n  " + "\n  ".join(bad))
+    print(f"[{name}] oracle == reference bit-for-bit on {len(DUMP)} quantities x {ref['SM'].shape}")
+
+
+def statics_of(cfgs):
+    return {k: np.array([float(c.get(k, 0.0 if k == "aspect" else 1.0 if k == "T_rain_snow" else np.nan))
+                         for c in cfgs]) for k in STATIC_KEYS}
+
+
+def save(name, cfgs, forcing, ref, keep=None, rows=None, extra=None):
+    d = {"forcing": forcing, "start_time": np.array(cfgs[0]["start_time"])}
+    d.update({f"static_{k}": v for k, v in statics_of(cfgs).items()})
+    keep = keep or DUMP
+    for k in keep:
+        d[f"ref_{k}"] = ref[k] if rows is None else ref[k][rows]
+    if rows is not None:
+        d["rows"] = rows
+    d.update(extra or {})
+    np.savez_compressed(HERE / f"{name}.npz", **d)
+    print(f"  wrote {name}.npz ({(HERE / f'{name}.npz').stat().st_size / 1024:.0f} KiB)")
+
+
+def main():
+    import tempfile
+
+    Bmi = install_reference()
+    tmp = Path(tempfile.mkdtemp())
+    samp = sample_forcing()
+
+    # 1. the reference's own integration test: 265 rows, sample_config
+    cfgs = [base_config()]
+    f = samp[:265, :, None]
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    gold = np.load(REF / "tests/data/output_m_total.npy").astype(np.float64)
+    mine = ref["M_total"][:, 0] * (cfgs[0]["da"] * 1e6)
+    print(f"[sample265] reference here vs upstream golden: max rel {np.max(np.abs(mine - gold) / np.abs(gold).max()):.2e},"
+          f" bit-equal {np.count_nonzero(mine == gold)}/265")
+    compare(ref, run_oracle(cfgs, f), "sample265")
+    save("sample265", cfgs, f, ref, extra={"upstream_output_m_total": gold})
+
+    # 2. four shipped catchments x 288 rows
+    cfgs = shipped_configs()
+    f = np.repeat(samp[:288, :, None], 4, axis=2)
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "cats288")
+    save("cats288", cfgs, f, ref)
+
+    # 3. const-forcing example
+    cfgs = [base_config(end_time="2013040500")]
+    f = samp[:288, :, None].copy()
+    f[:, 0, 0] = 3.0 * 10 ** (-3)
+    f[:, 1, 0] = -273.15 + (10.0 + 273.15)
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "const")
+    save("const", cfgs, f, ref)
+
+    # 4. fully constant forcing, thin snow: hand-over from snow melt to ice melt
+    cfgs = [base_config(h0_swe=0.01, h0_snow=0.2)]
+    f = np.tile(np.array([0.003, 10.0, 88000.0, 0.003, 2.0])[None, :, None], (96, 1, 1))
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "allconst")
+    save("allconst", cfgs, f, ref)
+
+    # 5. no snow, no ice
+    cfgs = [base_config(h0_snow=0.0, h0_ice=0.0, h0_swe=0.0, h0_iwe=0.0)]
+    f = np.tile(np.array([0.0, 5.0, 88000.0, 0.003, 2.0])[None, :, None], (3, 1, 1))
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    assert (ref["SM"] == 0).all() and (ref["IM"] == 0).all()
+    compare(ref, run_oracle(cfgs, f), "nosnow")
+    save("nosnow", cfgs, f, ref)
+
+    # 6. random cells
+    cfgs = random_cells()
+    rng = np.random.Generator(np.random.PCG64(7))
+    yr = synthetic_year(48, seed=99)
+    f = np.repeat(yr[:, :, None], len(cfgs), axis=2)
+    f[:, 1, :] += rng.normal(0, 3, (48, len(cfgs)))  # per-cell temperature spread around 0 degC
+    f[:, 0, :] *= rng.uniform(0, 3, (48, len(cfgs)))
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "rand64")
+    save("rand64", cfgs, f, ref)
+
+    # 7. one water year, four catchments, DST crossings
+    cfgs = [dict(c, start_time="2012100100", end_time="2013093023") for c in shipped_configs()]
+    yr = synthetic_year()
+    yr[:288] = samp[:288]
+    f = np.repeat(yr[:, :, None], 4, axis=2)
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "year4")
+    rows = np.unique(np.concatenate([np.arange(288), np.arange(288, 8760, 7), [8759]]))
+    keep = ["RH", "TSN_offset", "albedo", "n", "Qn_SW", "Qn_LW", "Qh", "Qe", "Q_sum", "SM", "IM", "M_total", "h_swe",
+            "h_iwe", "h_snow", "h_ice", "Eccs", "Ecci", "vol_P", "vol_PR", "vol_PS", "vol_SM", "vol_IM", "P_max"]
+    save("year4", cfgs, yr[:, :, None], ref, keep=keep, rows=rows)
+    print("all cases pinned")
+
+
+if __name__ == "__main__":
+    main()
