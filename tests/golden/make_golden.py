@@ -256,7 +256,7 @@ def main():
 
     # 4. fully constant forcing, thin snow: hand-over from snow melt to ice melt
     cfgs = [base_config(h0_swe=0.01, h0_snow=0.2)]
-    f = np.tile(np.array([0.003, 10.0, 88000.0, 0.003, 2.0])[None, :, None], (96, 1, 1))
+    f = np.tile(np.array([0.003, 10.0, 88000.0, 0.003, 6.0])[None, :, None], (96, 1, 1))
     ref = run_reference(Bmi, cfgs, f, tmp)
     compare(ref, run_oracle(cfgs, f), "allconst")
     save("allconst", cfgs, f, ref)

@@ -1,0 +1,73 @@
+"""Shared test plumbing: golden fixtures -> oracle / device engine, and the parity tolerances."""
+
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+STATIC_KEYS = ["da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow"]
+CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "year4"]
+
+# |gpu - ref| <= rtol*|ref| + atol, float64 modes (the atol of a flux is ~1e-12 x the size of
+# the terms that cancel in it, see DESIGN.md "Tolerances")
+RTOL = 1e-12
+ATOL = {
+    "p0": 0, "e_sat_air": 0, "e_air": 0, "RH": 0, "e_sat_surf": 0, "W_p": 0, "Dn": 0, "em_air": 0, "albedo": 0,
+    "n": 0, "snow3day": 1e-18, "P_rain": 0, "P_snow": 0, "TSN_offset": 1e-14,
+    "T_dew": 1e-12, "T_surf": 1e-12, "Ri": 1e-13, "Dh": 1e-15, "e_surf": 0,
+    "Qh": 1e-10, "Qe": 1e-10, "Qn_SW": 1e-10, "Qn_LW": 1e-10, "Q_sum": 1e-9,
+    "SM": 3e-18, "IM": 3e-18, "M_total": 3e-18,
+    "h_swe": 1e-14, "h_iwe": 1e-13, "h_snow": 2e-13, "h_ice": 1e-13, "Eccs": 1e-5, "Ecci": 1e-5,
+    "vol_P": 1e-9, "vol_PR": 1e-9, "vol_PS": 1e-9, "vol_SM": 1e-6, "vol_IM": 1e-6, "P_max": 0,
+}
+
+
+def load_case(name: str) -> dict:
+    z = np.load(GOLDEN / f"{name}.npz")
+    statics = {k: z[f"static_{k}"] for k in STATIC_KEYS}
+    N = statics["lat"].size
+    forcing = z["forcing"]
+    if forcing.shape[2] != N:
+        forcing = np.repeat(forcing, N, axis=2)
+    ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
+    rows = z["rows"] if "rows" in z.files else None
+    extra = {k: z[k] for k in z.files if k.startswith("upstream_")}
+    return {"name": name, "statics": statics, "N": N, "forcing": np.ascontiguousarray(forcing),
+            "start_time": str(z["start_time"]), "ref": ref, "rows": rows, **extra}
+
+
+def make_oracle(case: dict, strict_pow: bool = False, consts: dict | None = None):
+    from oracle.np_ref import CellStatics, Constants, OracleModel
+
+    s = case["statics"]
+    cells = CellStatics(**{k: s[k].astype(np.float64) for k in STATIC_KEYS}, tz=["America/Los_Angeles"])
+    return OracleModel(cells, Constants(**(consts or {})), start_time=case["start_time"], strict_pow=strict_pow)
+
+
+def default_constants() -> dict:
+    from topoflow_glacier_b200.config import _TABLE
+
+    return {k: v[1] for k, v in _TABLE.items() if v[1] is not ...}
+
+
+def make_engine(case: dict, mode: str = "f64", **kw):
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    consts = default_constants()
+    consts.update(kw.pop("consts", {}))
+    return MeltEngine(case["statics"], consts, case["start_time"], dt_hours=1, zones=["America/Los_Angeles"],
+                      mode=mode, horizon_steps=case["forcing"].shape[0] + 1, **kw)
+
+
+def err_report(got: np.ndarray, want: np.ndarray, atol: float, rtol: float = RTOL):
+    """(ok, worst ratio err/tol, max abs err, max rel err)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    both_nan = np.isnan(got) & np.isnan(want)
+    diff = np.where(both_nan, 0.0, np.abs(got - want))
+    tol = rtol * np.abs(want) + atol
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(diff == 0, 0.0, diff / np.where(tol > 0, tol, np.finfo(float).tiny))
+        rel = np.where(diff == 0, 0.0, diff / np.maximum(np.abs(want), 1e-300))
+    return bool((diff <= tol).all()), float(np.nanmax(ratio)), float(np.nanmax(diff)), float(np.nanmax(rel))

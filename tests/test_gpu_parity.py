@@ -1,0 +1,133 @@
+"""GPU: the CUDA path (through the C ABI, via MeltEngine.run -> tfg_run) against the oracle.
+
+Every case of tests/golden is run on the device with all intermediates recorded and compared with
+(a) the oracle run here on the same inputs and (b) the committed reference vectors.
+float64 modes: |gpu - ref| <= 1e-12*|ref| + atol(quantity)  (helpers.ATOL).
+"""
+
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import ATOL, CASES, RTOL, err_report, load_case, make_engine, make_oracle
+
+pytestmark = pytest.mark.gpu
+REPORT = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
+
+REC = ["h_snow", "h_swe", "SM", "h_ice", "h_iwe", "IM", "M_total", "RH", "p0", "e_sat_air", "e_air", "T_dew", "T_surf",
+       "e_sat_surf", "Ri", "Dn", "Dh", "Qh", "W_p", "e_surf", "Qe", "TSN_offset", "albedo", "n", "Qn_SW", "em_air",
+       "Qn_LW", "Q_sum", "Eccs", "Ecci", "snow3day", "P_rain", "P_snow"]
+VOLS = ["vol_P", "vol_PR", "vol_PS", "vol_SM", "vol_IM", "P_max"]
+
+
+def _oracle_series(case):
+    ora = make_oracle(case, strict_pow=case["N"] <= 4)
+    T = case["forcing"].shape[0]
+    out = {k: np.empty((T, case["N"])) for k in REC}
+    for t in range(T):
+        d = ora.step(*case["forcing"][t])
+        for k in REC:
+            out[k][t] = d[k]
+    out.update({k: getattr(ora, k) for k in VOLS})
+    return out
+
+
+_ORACLE = {}
+
+
+def oracle_series(name):
+    if name not in _ORACLE:
+        _ORACLE[name] = (load_case(name), None)
+        _ORACLE[name] = (_ORACLE[name][0], _oracle_series(_ORACLE[name][0]))
+    return _ORACLE[name]
+
+
+def _dump(tag, rep):
+    REPORT.mkdir(exist_ok=True)
+    p = REPORT / "parity_report.json"
+    cur = json.loads(p.read_text()) if p.exists() else {}
+    cur[tag] = rep
+    p.write_text(json.dumps(cur, indent=1, sort_keys=True))
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+@pytest.mark.parametrize("name", CASES)
+def test_fused_run_matches_oracle(name, mode, cuda_device):
+    import torch
+
+    case, want = oracle_series(name)
+    eng = make_engine(case, mode=mode)
+    forcing = torch.as_tensor(case["forcing"]).to(cuda_device)
+    got = eng.run(forcing, record=REC)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in got.items()}
+    got.update({k: eng.row(k).cpu().numpy() for k in VOLS})
+    rep, bad = {}, []
+    for k in REC + VOLS:
+        ok, ratio, dabs, drel = err_report(got[k], want[k], ATOL[k])
+        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            t = int(np.argmax(np.abs(got[k] - want[k]).reshape(len(got[k]), -1).max(axis=1))) if got[k].ndim == 2 else -1
+            bad.append((k, ratio, dabs, drel, t))
+    # and against the committed reference vectors (made on the build machine)
+    rows = case["rows"] if case["rows"] is not None else slice(None)
+    for k, ref in case["ref"].items():
+        g = got[k][rows] if k in REC else got[k]
+        r = ref if k in REC else ref[-1]
+        ok, ratio, dabs, drel = err_report(g, r, ATOL[k])
+        rep["golden:" + k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            bad.append(("golden:" + k, ratio, dabs, drel, -1))
+    _dump(f"{name}/{mode}", rep)
+    eng.close()
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast", "f32"])
+def test_single_steps_equal_fused_run(mode, cuda_device):
+    """n_steps=1 launches (exact window re-sum, state through HBM every step) == one fused launch, bit for bit."""
+    import torch
+
+    case = load_case("rand64")
+    T = case["forcing"].shape[0]
+    a, b = make_engine(case, mode=mode), make_engine(case, mode=mode)
+    forcing = torch.as_tensor(case["forcing"]).to(cuda_device, a.dtype)
+    a.run(forcing)
+    for t in range(T):
+        b.run(forcing[t:t + 1].contiguous(), 1)
+    # and a split into uneven chunks (window seeded from HBM at each launch)
+    c = make_engine(case, mode=mode)
+    done = 0
+    for k in (5, 1, 17, T - 23):
+        c.run(forcing[done:done + k].contiguous(), k)
+        done += k
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state) and torch.equal(a.ring, b.ring)
+    assert torch.equal(a.state, c.state) and torch.equal(a.ring, c.ring)
+    for e in (a, b, c):
+        e.close()
+
+
+def test_f32_mode_tolerance(cuda_device):
+    """fp32 mode has its own, looser, stated tolerance: fluxes 2e-3 rel + 0.05 W m-2, depths 1e-3 rel."""
+    import torch
+
+    case, want = oracle_series("cats288")
+    eng = make_engine(case, mode="f32")
+    forcing = torch.as_tensor(case["forcing"]).to(cuda_device, torch.float32)
+    got = {k: v.cpu().numpy().astype(np.float64) for k, v in eng.run(forcing, record=REC).items()}
+    rep = {}
+    tol = {"Qn_SW": (2e-3, 0.05), "Qn_LW": (2e-3, 0.05), "Qh": (2e-3, 0.05), "Qe": (2e-3, 0.05), "Q_sum": (2e-3, 0.2),
+           "RH": (1e-4, 0), "h_swe": (1e-3, 1e-5), "h_iwe": (1e-3, 1e-5), "M_total": (5e-3, 1e-9), "albedo": (1e-5, 0)}
+    bad = []
+    for k, (rt, at) in tol.items():
+        ok, ratio, dabs, drel = err_report(got[k], want[k], at, rt)
+        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            bad.append((k, ratio, dabs, drel))
+    _dump("cats288/f32", rep)
+    eng.close()
+    assert not bad, bad

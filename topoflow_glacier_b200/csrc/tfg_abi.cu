@@ -1,0 +1,378 @@
+// tfg_abi.cu -- the extern "C" surface of libtfglacier.so (include/tfglacier.h): context, binding,
+// dispatch of the fused melt kernel, forcing ingestion/conversion and the synthetic-forcing generator.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "tfg_run.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) {
+    g_err += ": ";
+    g_err += cudaGetErrorString(e);
+  }
+  return -1;
+}
+
+#define TFG_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return fail(#call, e__);     \
+  } while (0)
+
+}  // namespace
+
+struct tfg_ctx {
+  int device = 0;
+  int mode = TFG_F64_STRICT;
+  bool have_consts = false, have_static = false, have_state = false;
+  tfg_constants c{};
+  tfg_statics s{};
+  tfg_state st{};
+  int64_t n_cells = 0;
+  // device copies of the host time tables (owned by the library)
+  void* d_rows = nullptr;
+  void* d_gmt = nullptr;
+  int64_t n_time = 0;
+  int n_tz = 1;
+};
+
+namespace {
+
+template <class raw>
+tfg::Consts<raw> derive(const tfg_constants& c) {
+  // every product / ratio is formed exactly as the reference forms it (file:line in tfg_physics.cuh)
+  tfg::Consts<double> k;
+  k.dt = c.dt_hours;
+  k.days_per_dt = c.dt_hours / 86400.0;
+  k.T0 = c.T0;
+  k.sea_p0 = c.sea_level_p0;
+  k.r_star = c.uni_gas_const;
+  k.eps = c.eps;
+  k.one_m_eps = 1.0 - c.eps;
+  k.gz = c.g * c.z_wind;
+  k.z = c.z_wind;
+  k.z0_air = c.z0_air;
+  k.kappa = c.kappa;
+  k.rho_cp_air = c.rho_air * c.Cp_air;
+  k.rho_lv_air = c.rho_air * c.Lv;
+  k.lhc = c.latent_heat_constant;
+  k.ws_ratio = c.rho_H2O / c.rho_snow;
+  k.wi_ratio = c.rho_H2O / c.rho_ice;
+  k.rho_cp_snow = c.rho_snow * c.Cp_snow;
+  k.rho_lf = c.rho_H2O * c.Lf;
+  k.dust = c.dust_atten;
+  k.emis_a = (1.0 - c.canopy_factor) * 1.72;
+  k.emis_b = 1.0 + (0.22 * (c.cloud_factor * c.cloud_factor));
+  k.canopy = c.canopy_factor;
+  k.sigma = c.sigma;
+  k.es_sigma = c.em_surf * c.sigma;
+  k.one_m_es = 1.0 - c.em_surf;
+  k.one_seventh = 1.0 / 7.0;
+  const double pi = 3.141592653589793;
+  k.omega = (360.0 / 24.0) * (pi / 180.0);
+  k.rad2deg = 180.0 / pi;
+  k.deg2rad = pi / 180.0;
+  k.satterlund = c.satterlund;
+  tfg::Consts<raw> r;
+#define CP(f) r.f = static_cast<raw>(k.f)
+  CP(dt); CP(days_per_dt); CP(T0); CP(sea_p0); CP(r_star); CP(eps); CP(one_m_eps); CP(gz); CP(z); CP(z0_air);
+  CP(kappa); CP(rho_cp_air); CP(rho_lv_air); CP(lhc); CP(ws_ratio); CP(wi_ratio); CP(rho_cp_snow); CP(rho_lf);
+  CP(dust); CP(emis_a); CP(emis_b); CP(canopy); CP(sigma); CP(es_sigma); CP(one_m_es); CP(one_seventh); CP(omega);
+  CP(rad2deg); CP(deg2rad);
+#undef CP
+  r.satterlund = k.satterlund;
+  return r;
+}
+
+template <class raw>
+tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, void* record,
+                                uint64_t mask, double* agg, int32_t n_basin) {
+  tfg::RunParams<raw> p{};
+  p.n_cells = x->n_cells;
+  p.step0 = step0;
+  p.n_steps = n_steps;
+  p.ring_slots = x->c.ring_slots;
+  p.n_tz = x->n_tz;
+  p.exact_ring = (n_steps == 1);
+  p.forcing = static_cast<const raw*>(forcing);
+#define S(f) p.f = static_cast<const raw*>(x->s.f)
+  S(a_elev); S(sin_lat); S(cos_lat); S(neg_tan_lat); S(lon); S(dlon); S(t_noon); S(da_m2);
+#undef S
+  p.sin_eq = static_cast<const raw*>(x->s.sin_lat_eq);
+  p.cos_eq = static_cast<const raw*>(x->s.cos_lat_eq);
+  p.neg_tan_eq = static_cast<const raw*>(x->s.neg_tan_lat_eq);
+  p.t_rs = static_cast<const raw*>(x->s.t_rain_snow);
+  p.basin_id = x->s.basin_id;
+  p.tz_idx = x->s.tz_idx;
+#define T(f) p.f = static_cast<raw*>(x->st.f)
+  T(h_snow); T(h_swe); T(h_ice); T(h_iwe); T(eccs); T(ecci); T(albedo); T(n_days); T(SM); T(IM); T(M_total); T(RH);
+  T(vol_P); T(vol_PR); T(vol_PS); T(vol_SM); T(vol_IM); T(P_max); T(ring);
+#undef T
+  p.rows = static_cast<const tfg::TimeRow<raw>*>(x->d_rows);
+  p.gmt = static_cast<const raw*>(x->d_gmt);
+  p.record = static_cast<raw*>(record);
+  p.record_mask = mask;
+  p.n_rec = __builtin_popcountll(mask);
+  p.basin_agg = agg;
+  p.n_basin = n_basin;
+  p.k = derive<raw>(x->c);
+  return p;
+}
+
+// ---- K2: raw met columns -> live forcings (examples/run_topoflow_glacier.py:40-73) -------------------
+template <class raw>
+__global__ void convert_kernel(const double* __restrict__ in, raw* __restrict__ out, int64_t n_steps, int64_t N) {
+  const int64_t total = n_steps * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / N, c = i - t * N;
+    const double* r = in + t * 6 * N + c;
+    const double rain = r[0], t2d = r[N], psfc = r[2 * N], q2d = r[3 * N], u = r[4 * N], v = r[5 * N];
+    raw* o = out + t * TFG_N_FORCING * N + c;
+    o[0] = (raw)__dmul_rn(rain, 0.001);                         // precip * 10**(-3)
+    o[N] = (raw)__dadd_rn(-273.15, t2d);                        // K_to_C + T2D
+    o[2 * N] = (raw)psfc;
+    o[3 * N] = (raw)q2d;
+    o[4 * N] = (raw)__dsqrt_rn(__dadd_rn(__dmul_rn(u, u), __dmul_rn(v, v)));  // (U**2 + V**2) ** 0.5
+  }
+}
+
+// ---- synthetic forcing (bench only): Philox4x32-10 keyed by (seed, cell, step) ------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+template <class raw>
+__global__ void synth_kernel(raw* __restrict__ out, const raw* __restrict__ elev, int64_t step0, int32_t n_steps,
+                             int64_t N, uint64_t seed) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const float lapse = -6.5e-3f * ((float)elev[c] - 2400.0f);
+  for (int t = 0; t < n_steps; ++t) {
+    const int64_t step = step0 + t;
+    uint32_t a[4], b[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+    // Box-Muller pairs
+    const float r0 = sqrtf(-2.0f * __logf(u01(a[0]))), r1 = sqrtf(-2.0f * __logf(u01(a[2])));
+    float s0, c0, s1, c1;
+    __sincosf(6.2831853f * u01(a[1]), &s0, &c0);
+    __sincosf(6.2831853f * u01(a[3]), &s1, &c1);
+    const float nT = r0 * c0, nP = r0 * s0, nU = r1 * c1, nV = r1 * s1;
+    const int hour = (int)(step % 24);
+    const int doy = (int)((274 + step / 24) % 365);
+    const float T2D = 273.15f + 2.0f + 9.0f * __sinf(6.2831853f * (float)(doy - 105) / 365.0f) +
+                      4.0f * __sinf(6.2831853f * (float)(hour - 15) / 24.0f) + 2.0f * nT + lapse;
+    const float PSFC = 88900.0f + 400.0f * nP;
+    const float Tc = T2D - 273.15f;
+    const float esat = 611.0f * __expf(17.3f * Tc / (Tc + 237.3f));
+    const float qsat = 0.622f * esat / (PSFC - 0.378f * esat);
+    const float q = fminf(fmaxf(0.8f * qsat * (0.5f + 0.5f * u01(b[0])), 5e-4f), 0.012f);
+    const float rain = (u01(b[1]) < 0.12f) ? -0.5f * __logf(u01(b[2])) : 0.0f;  // mm/h
+    raw* o = out + (int64_t)t * TFG_N_FORCING * N + c;
+    o[0] = (raw)((double)rain * 0.001);
+    o[N] = (raw)((double)T2D - 273.15);
+    o[2 * N] = (raw)PSFC;
+    o[3 * N] = (raw)q;
+    o[4 * N] = (raw)(3.0f * sqrtf(nU * nU + nV * nV));
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfg_abi_version(void) { return TFG_ABI_VERSION; }
+const char* tfg_last_error(void) { return g_err.c_str(); }
+
+int tfg_create(tfg_ctx** out, int device, int mode) {
+  if (!out) return fail("tfg_create: out is NULL");
+  if (mode != TFG_F64_STRICT && mode != TFG_F64_FAST && mode != TFG_F32) return fail("tfg_create: unknown mode");
+  int n = 0;
+  TFG_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail("tfg_create: no such CUDA device");
+  TFG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TFG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("tfg_create: libtfglacier is built for sm_100a (B200) only");
+  tfg_ctx* x = new tfg_ctx();
+  x->device = device;
+  x->mode = mode;
+  *out = x;
+  return 0;
+}
+
+void tfg_destroy(tfg_ctx* x) {
+  if (!x) return;
+  cudaSetDevice(x->device);
+  if (x->d_rows) cudaFree(x->d_rows);
+  if (x->d_gmt) cudaFree(x->d_gmt);
+  delete x;
+}
+
+int tfg_mode(const tfg_ctx* x) { return x ? x->mode : -1; }
+size_t tfg_elem_size(const tfg_ctx* x) { return (x && x->mode == TFG_F32) ? 4 : 8; }
+
+int tfg_set_constants(tfg_ctx* x, const tfg_constants* c) {
+  if (!x || !c) return fail("tfg_set_constants: NULL argument");
+  if (!(c->dt_hours > 0)) return fail("tfg_set_constants: dt_hours must be > 0");
+  if (c->ring_slots < 1 || c->ring_slots > TFG_RING_SLOTS_MAX) return fail("tfg_set_constants: bad ring_slots");
+  x->c = *c;
+  x->have_consts = true;
+  return 0;
+}
+
+int tfg_bind_static(tfg_ctx* x, int64_t n_cells, const tfg_statics* s) {
+  if (!x || !s) return fail("tfg_bind_static: NULL argument");
+  if (n_cells <= 0) return fail("tfg_bind_static: n_cells must be > 0");
+  const void* req[] = {s->a_elev, s->sin_lat, s->cos_lat, s->neg_tan_lat, s->lon, s->sin_lat_eq, s->cos_lat_eq,
+                       s->neg_tan_lat_eq, s->dlon, s->t_noon, s->da_m2, s->t_rain_snow};
+  for (const void* p : req)
+    if (!p) return fail("tfg_bind_static: a required table is NULL");
+  x->s = *s;
+  x->n_cells = n_cells;
+  x->have_static = true;
+  return 0;
+}
+
+int tfg_bind_state(tfg_ctx* x, const tfg_state* s) {
+  if (!x || !s) return fail("tfg_bind_state: NULL argument");
+  void* req[] = {s->h_snow, s->h_swe, s->h_ice, s->h_iwe, s->eccs, s->ecci, s->albedo, s->n_days,
+                 s->SM, s->IM, s->M_total, s->RH, s->ring};
+  for (void* p : req)
+    if (!p) return fail("tfg_bind_state: a required array is NULL");
+  void* vol[] = {s->vol_P, s->vol_PR, s->vol_PS, s->vol_SM, s->vol_IM, s->P_max};
+  int nv = 0;
+  for (void* p : vol) nv += (p != nullptr);
+  if (nv != 0 && nv != 6) return fail("tfg_bind_state: pass all six diagnostic integrals or none");
+  x->st = *s;
+  x->have_state = true;
+  return 0;
+}
+
+int tfg_bind_time(tfg_ctx* x, const tfg_time_row* rows, const double* gmt, int64_t n_steps, int n_tz, void* stream) {
+  if (!x || !rows || !gmt) return fail("tfg_bind_time: NULL argument");
+  if (n_steps <= 0 || n_tz < 1 || n_tz > TFG_MAX_TZ) return fail("tfg_bind_time: bad n_steps / n_tz");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t es = tfg_elem_size(x);
+  void *d_rows = nullptr, *d_gmt = nullptr;
+  TFG_CUDA(cudaMalloc(&d_rows, (size_t)n_steps * 6 * es));
+  TFG_CUDA(cudaMalloc(&d_gmt, (size_t)n_steps * n_tz * es));
+  if (x->mode == TFG_F32) {
+    std::string buf((size_t)n_steps * (6 + n_tz) * sizeof(float), '\0');
+    float* fr = reinterpret_cast<float*>(&buf[0]);
+    float* fg = fr + (size_t)n_steps * 6;
+    const double* src = reinterpret_cast<const double*>(rows);
+    for (int64_t i = 0; i < n_steps * 6; ++i) fr[i] = (float)src[i];
+    for (int64_t i = 0; i < n_steps * n_tz; ++i) fg[i] = (float)gmt[i];
+    TFG_CUDA(cudaMemcpyAsync(d_rows, fr, (size_t)n_steps * 6 * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaMemcpyAsync(d_gmt, fg, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaStreamSynchronize(s));
+  } else {
+    TFG_CUDA(cudaMemcpyAsync(d_rows, rows, (size_t)n_steps * 6 * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaMemcpyAsync(d_gmt, gmt, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaStreamSynchronize(s));
+  }
+  // kernels already queued may still read the old tables: free them only after the device drained
+  if (x->d_rows || x->d_gmt) {
+    TFG_CUDA(cudaDeviceSynchronize());
+    cudaFree(x->d_rows);
+    cudaFree(x->d_gmt);
+  }
+  x->d_rows = d_rows;
+  x->d_gmt = d_gmt;
+  x->n_time = n_steps;
+  x->n_tz = n_tz;
+  return 0;
+}
+
+int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, void* record, uint64_t record_mask,
+            double* basin_agg, int32_t n_basin, void* stream) {
+  if (!x || !forcing) return fail("tfg_run: NULL argument");
+  if (!x->have_consts || !x->have_static || !x->have_state || !x->d_rows)
+    return fail("tfg_run: constants, statics, state and time tables must be bound first");
+  if (n_steps <= 0 || step0 < 0) return fail("tfg_run: bad step range");
+  if (step0 + n_steps > x->n_time) return fail("tfg_run: step range exceeds the bound time table");
+  if (record && (record_mask == 0 || (record_mask >> TFG_REC_COUNT) != 0)) return fail("tfg_run: bad record_mask");
+  if (basin_agg && (n_basin <= 0 || !x->s.basin_id)) return fail("tfg_run: aggregates need basin_id and n_basin");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool rec = record != nullptr, agg = basin_agg != nullptr, vol = x->st.vol_P != nullptr;
+  cudaError_t e;
+  if (x->mode == TFG_F32) {
+    e = tfg::launch_run_f32(make_params<float>(x, forcing, step0, n_steps, record, record_mask, basin_agg, n_basin),
+                            rec, agg, vol, s);
+  } else {
+    auto p = make_params<double>(x, forcing, step0, n_steps, record, record_mask, basin_agg, n_basin);
+    e = (x->mode == TFG_F64_STRICT) ? tfg::launch_run_strict(p, rec, agg, vol, s)
+                                    : tfg::launch_run_fast(p, rec, agg, vol, s);
+  }
+  if (e != cudaSuccess) return fail("tfg_run: kernel launch", e);
+  return 0;
+}
+
+int tfg_ingest_async(tfg_ctx* x, const void* pinned_src, void* dev_dst, size_t bytes, void* stream, void* done_event) {
+  if (!x || !pinned_src || !dev_dst) return fail("tfg_ingest_async: NULL argument");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TFG_CUDA(cudaMemcpyAsync(dev_dst, pinned_src, bytes, cudaMemcpyHostToDevice, s));
+  if (done_event) TFG_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(done_event), s));
+  return 0;
+}
+
+int tfg_stream_wait_event(tfg_ctx* x, void* stream, void* event) {
+  if (!x || !event) return fail("tfg_stream_wait_event: NULL argument");
+  TFG_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0));
+  return 0;
+}
+
+int tfg_convert_forcing(tfg_ctx* x, const double* raw, void* out, int64_t n_steps, int64_t n_cells, void* stream) {
+  if (!x || !raw || !out) return fail("tfg_convert_forcing: NULL argument");
+  if (n_steps <= 0 || n_cells <= 0) return fail("tfg_convert_forcing: empty block");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = n_steps * n_cells;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (x->mode == TFG_F32) convert_kernel<float><<<grid, 256, 0, s>>>(raw, static_cast<float*>(out), n_steps, n_cells);
+  else convert_kernel<double><<<grid, 256, 0, s>>>(raw, static_cast<double*>(out), n_steps, n_cells);
+  TFG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tfg_synth_forcing(tfg_ctx* x, void* forcing, int64_t step0, int32_t n_steps, int64_t n_cells, const void* elev,
+                      uint64_t seed, void* stream) {
+  if (!x || !forcing || !elev) return fail("tfg_synth_forcing: NULL argument");
+  if (n_steps <= 0 || n_cells <= 0) return fail("tfg_synth_forcing: empty block");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((n_cells + 255) / 256);
+  if (x->mode == TFG_F32)
+    synth_kernel<float><<<grid, 256, 0, s>>>(static_cast<float*>(forcing), static_cast<const float*>(elev), step0,
+                                             n_steps, n_cells, seed);
+  else
+    synth_kernel<double><<<grid, 256, 0, s>>>(static_cast<double*>(forcing), static_cast<const double*>(elev), step0,
+                                              n_steps, n_cells, seed);
+  TFG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// tfg_num.cuh -- scalar types for the three arithmetic modes of the melt kernels.
+//
+// The physics (tfg_physics.cuh) is written once against Num<P>.  The policy P decides how an
+// expression is evaluated:
+//   StrictF64  every + - * / sqrt is a single IEEE round-to-nearest operation issued through the
+//              __d*_rn intrinsics, which nvcc never contracts into FMAs.  Together with
+//              host-precomputed constants this makes the non-transcendental part of a step
+//              bit-identical to the NumPy reference; only exp/log/pow/atan/acos/sin/cos ulps differ.
+//   FastF64    plain double arithmetic (FMA contraction allowed), cheaper formulations of pow.
+//   FastF32    float with MUFU-backed intrinsics.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace tfg {
+
+struct StrictF64 { using raw = double; static constexpr bool strict = true;  static constexpr bool f32 = false; };
+struct FastF64   { using raw = double; static constexpr bool strict = false; static constexpr bool f32 = false; };
+struct FastF32   { using raw = float;  static constexpr bool strict = false; static constexpr bool f32 = true;  };
+
+template <class P>
+struct Num {
+  using raw = typename P::raw;
+  raw v;
+  __host__ __device__ Num() {}
+  __host__ __device__ constexpr Num(double x) : v(static_cast<raw>(x)) {}
+  __host__ __device__ constexpr Num(float x) : v(static_cast<raw>(x)) {}
+  __host__ __device__ constexpr Num(int x) : v(static_cast<raw>(x)) {}
+};
+
+// ---- arithmetic ----------------------------------------------------------------------------------
+template <class P> __device__ __forceinline__ Num<P> operator+(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>(__dadd_rn(a.v, b.v)); else return Num<P>(a.v + b.v);
+}
+template <class P> __device__ __forceinline__ Num<P> operator-(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>(__dsub_rn(a.v, b.v)); else return Num<P>(a.v - b.v);
+}
+template <class P> __device__ __forceinline__ Num<P> operator*(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>(__dmul_rn(a.v, b.v)); else return Num<P>(a.v * b.v);
+}
+template <class P> __device__ __forceinline__ Num<P> operator/(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>(__ddiv_rn(a.v, b.v));
+  else if constexpr (P::f32) return Num<P>(__fdividef(a.v, b.v));
+  else return Num<P>(a.v / b.v);
+}
+template <class P> __device__ __forceinline__ Num<P> operator-(Num<P> a) { return Num<P>(-a.v); }
+
+#define TFG_MIXED(op)                                                                                         \
+  template <class P> __device__ __forceinline__ Num<P> operator op(Num<P> a, double b) { return a op Num<P>(b); } \
+  template <class P> __device__ __forceinline__ Num<P> operator op(double a, Num<P> b) { return Num<P>(a) op b; }
+TFG_MIXED(+) TFG_MIXED(-) TFG_MIXED(*) TFG_MIXED(/)
+#undef TFG_MIXED
+
+#define TFG_CMP(op)                                                                                      \
+  template <class P> __device__ __forceinline__ bool operator op(Num<P> a, Num<P> b) { return a.v op b.v; } \
+  template <class P> __device__ __forceinline__ bool operator op(Num<P> a, double b) {                  \
+    return a.v op static_cast<typename P::raw>(b);                                                       \
+  }
+TFG_CMP(<) TFG_CMP(<=) TFG_CMP(>) TFG_CMP(>=) TFG_CMP(==) TFG_CMP(!=)
+#undef TFG_CMP
+
+template <class P> __device__ __forceinline__ Num<P> sel(bool c, Num<P> a, Num<P> b) { return c ? a : b; }
+
+// np.minimum / np.maximum propagate NaN; fmin/fmax do not.  Strict mode keeps NumPy's behaviour.
+template <class P> __device__ __forceinline__ Num<P> nmax(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>((a.v >= b.v) ? a.v : ((b.v > a.v) ? b.v : a.v + b.v));
+  else if constexpr (P::f32) return Num<P>(fmaxf(a.v, b.v));
+  else return Num<P>(fmax(a.v, b.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nmin(Num<P> a, Num<P> b) {
+  if constexpr (P::strict) return Num<P>((a.v <= b.v) ? a.v : ((b.v < a.v) ? b.v : a.v + b.v));
+  else if constexpr (P::f32) return Num<P>(fminf(a.v, b.v));
+  else return Num<P>(fmin(a.v, b.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nabs(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(fabsf(a.v)); else return Num<P>(fabs(a.v));
+}
+
+// ---- transcendental functions ----------------------------------------------------------------------
+template <class P> __device__ __forceinline__ Num<P> nsqrt(Num<P> a) {
+  if constexpr (P::strict) return Num<P>(__dsqrt_rn(a.v));
+  else if constexpr (P::f32) return Num<P>(__fsqrt_rn(a.v));
+  else return Num<P>(sqrt(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nexp(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(__expf(a.v)); else return Num<P>(exp(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nlog(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(__logf(a.v)); else return Num<P>(log(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nsin(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(__sinf(a.v)); else return Num<P>(sin(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> ncos(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(__cosf(a.v)); else return Num<P>(cos(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> natan(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(atanf(a.v)); else return Num<P>(atan(a.v));
+}
+template <class P> __device__ __forceinline__ Num<P> nacos(Num<P> a) {
+  if constexpr (P::f32) return Num<P>(acosf(a.v)); else return Num<P>(acos(a.v));
+}
+// x**y for x > 0.  Strict: libdevice pow (NumPy calls its own / libm's pow).  Fast: exp(y*log(x)),
+// whose relative error is ~|y*log(x)| ulp -- far inside the 1e-12 budget for the exponents used here.
+template <class P> __device__ __forceinline__ Num<P> npow(Num<P> x, Num<P> y) {
+  if constexpr (P::strict) return Num<P>(pow(x.v, y.v));
+  else if constexpr (P::f32) return Num<P>(__expf(y.v * __logf(x.v)));
+  else return Num<P>(exp(y.v * log(x.v)));
+}
+template <class P> __device__ __forceinline__ Num<P> npow4(Num<P> x) {  // x**4.0
+  if constexpr (P::strict) return Num<P>(pow(x.v, 4.0));
+  else { auto s = x.v * x.v; return Num<P>(s * s); }
+}
+template <class P> __device__ __forceinline__ Num<P> npow15(Num<P> x) {  // x**1.5
+  if constexpr (P::strict) return Num<P>(pow(x.v, 1.5));
+  else return x * nsqrt(x);
+}
+
+}  // namespace tfg

@@ -1,0 +1,300 @@
+// tfg_physics.cuh -- one cell, one timestep of the energy-balance + melt update.
+//
+// Restates BmiTopoflowGlacier.update() (reference src/topoflow_glacier/bmi/bmi_topoflow_glacier.py:413-465)
+// and Clear_Sky_Radiation (reference src/topoflow_glacier/physics/solar_funcs.py:894-953) as a single
+// device function.  Quantities that depend on the clock only arrive in TimeRow, quantities that depend on the
+// cell only in CellStatic; both are evaluated on the host with the reference's scalar expressions.
+// In StrictF64 mode every operation keeps the reference's order and association (line numbers in comments).
+#pragma once
+#include "tfg_num.cuh"
+
+namespace tfg {
+
+// host-precomputed scalars (products/ratios formed in the reference's own order)
+template <class raw>
+struct Consts {
+  raw dt;            // cfg.dt [h]
+  raw days_per_dt;   // dt / 86400 (sic, :287)
+  raw T0;
+  raw sea_p0;        // :539
+  raw r_star;        // :543
+  raw eps, one_m_eps;  // :817
+  raw gz;            // g * z  (:640)
+  raw z, z0_air, kappa;  // :670
+  raw rho_cp_air;    // rho_air * Cp_air (:745)
+  raw rho_lv_air;    // rho_air * Lv (:932)
+  raw lhc;           // latent_heat_constant (:931)
+  raw ws_ratio;      // rho_H2O / rho_snow (:385, :1030)
+  raw wi_ratio;      // rho_H2O / rho_ice
+  raw rho_cp_snow;   // rho_snow * Cp_snow (:1533)
+  raw rho_lf;        // rho_H2O * Lf (:1368)
+  raw dust;          // cfg.dust_atten
+  raw emis_a;        // (1 - F) * 1.72 (:1179)
+  raw emis_b;        // 1 + 0.22 * C**2 (:1180)
+  raw canopy;        // F
+  raw sigma;         // :1234
+  raw es_sigma;      // em_surf * sigma (:1236)
+  raw one_m_es;      // 1 - em_surf (:1246)
+  raw one_seventh;   // :292
+  raw omega;         // 15 deg/h in rad (solar_funcs.py:257-258)
+  raw rad2deg;       // 180 / pi (solar_funcs.py:550)
+  raw deg2rad;       // pi / 180 (solar_funcs.py:566)
+  int satterlund;
+};
+
+template <class raw>
+struct TimeRow {  // see tfg_time_row in include/tfglacier.h
+  raw clock_hour, TE, sin_decl, cos_decl, tan_decl, isc_e0;
+};
+
+template <class raw>
+struct CellStatic {
+  raw a_elev, sin_lat, cos_lat, neg_tan_lat, sin_eq, cos_eq, neg_tan_eq, dlon, t_noon, da_m2, t_rs;
+};
+
+template <class raw>
+struct CellState {
+  raw h_snow, h_swe, h_ice, h_iwe, eccs, ecci, albedo, n_days;
+};
+
+template <class raw>
+struct CellVol {  // diagnostic time integrals, :558-624, :1482-1494
+  raw vol_P, vol_PR, vol_PS, vol_SM, vol_IM, P_max;
+};
+
+template <class raw>
+struct StepOut {
+  raw SM, IM, M_total, RH;
+  // intermediates (only stored when the caller records them)
+  raw p0, e_sat_air, e_air, T_dew, T_surf, e_sat_surf, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, th, Qn_SW, em_air, Qn_LW,
+      Q_sum, P_rain, P_snow;
+};
+
+// update_saturation_vapor_pressure(MBAR=True), :784-802
+template <class P>
+__device__ __forceinline__ Num<P> e_sat_mbar(const Consts<typename P::raw>& k, Num<P> T) {
+  using R = Num<P>;
+  R e_sat;
+  if (!k.satterlund) {
+    R term1 = (R(17.3) * T) / (T + 237.3);
+    e_sat = R(0.611) * nexp(term1);
+  } else {
+    R term1 = R(2353.0) / (T + 273.15);
+    e_sat = npow(R(10.0), R(11.4) - term1) / 1000.0;
+  }
+  return e_sat * 10.0;
+}
+
+// The clock- and cell-dependent part of Clear_Sky_Radiation; returns K_cs.
+template <class P>
+__device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
+                                            const CellStatic<typename P::raw>& s, Num<P> th, Num<P> W_p,
+                                            Num<P> albedo) {
+  using R = Num<P>;
+  const R sin_d(tr.sin_decl), cos_d(tr.cos_decl), tan_d(tr.tan_decl), omega(k.omega);
+  const R wt = omega * th;
+  const R c_wt = ncos(wt);                                   // cos(omega*th), solar_funcs.py:282, :391
+  const R c_u = ncos(wt + R(s.dlon));                        // solar_funcs.py:867
+  // sunrise / sunset arguments, solar_funcs.py:325-326 (horizontal) and :796 (equivalent latitude)
+  const R arg_eq = nmin(nmax(R(-1.0), R(s.neg_tan_eq) * tan_d), R(1.0));
+  const R arg_h = nmin(nmax(R(-1.0), R(s.neg_tan_lat) * tan_d), R(1.0));
+  bool dark;
+  if constexpr (P::strict) {
+    // T_sr / T_ss exactly as solar_funcs.py:783-830, then the comparison of :939
+    const R q_eq = nacos(arg_eq) / omega;
+    const R q_h = nacos(arg_h) / omega;
+    const R T_sr = nmax((-q_eq) + R(s.t_noon), -q_h);
+    const R T_ss = nmin(q_eq + R(s.t_noon), q_h);
+    dark = (th <= T_sr) || (th >= T_ss);
+  } else {
+    // th <= -acos(a)/omega  or  th >= acos(a)/omega   <=>   cos(omega*th) <= a   for |omega*th| < pi;
+    // outside that range both reference comparisons are true anyway (|T_sr|,|T_ss| <= 12 h).
+    const R pi(3.141592653589793);
+    dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (nabs(wt) >= pi) || (nabs(wt + R(s.dlon)) >= pi);
+  }
+  if (dark) return R(0.0);                                   // solar_funcs.py:940-941
+
+  // Zenith_Angle solar_funcs.py:281-284
+  const R cosZ = (R(s.sin_lat) * sin_d) + ((R(s.cos_lat) * cos_d) * c_wt);
+  const R Z = nacos(cosZ);
+  // Optical_Air_Mass solar_funcs.py:549-568 (Kasten & Young 1989)
+  R gamma = R(90.0) - (Z * R(k.rad2deg));
+  gamma = sel(R(0.0) > gamma, R(0.0), gamma);
+  R t1;
+  if constexpr (P::strict) t1 = nsin(gamma * R(k.deg2rad));
+  else t1 = nmax(cosZ, R(0.0));                              // sin(90deg - Z) == cos Z
+  const R t2 = R(0.50572) / npow(gamma + 6.07995, R(1.6364));
+  const R M_opt = R(1.0) / (t1 + t2);
+  // Atmospheric_Transmissivity solar_funcs.py:608-614
+  const R a_sa = R(-0.1240) - (R(0.0207) * W_p);
+  const R b_sa = R(-0.0682) - (R(0.0248) * W_p);
+  const R tau = nmin(nmax(nexp(a_sa + (b_sa * M_opt)) - R(k.dust), R(0.0)), R(1.0));
+  // Scattering_Attenuation solar_funcs.py:649-653
+  const R a_s = R(-0.0363) - (R(0.0084) * W_p);
+  const R b_s = R(-0.0572) - (R(0.0173) * W_p);
+  const R gam_s = (R(1.0) - nexp(a_s + (b_s * M_opt))) + R(k.dust);
+  // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
+  const R isc_e0(tr.isc_e0);
+  const R K_h = nmax(isc_e0 * (((cos_d * R(s.cos_lat)) * c_wt) + (sin_d * R(s.sin_lat))), R(0.0));
+  const R K_s = nmax(isc_e0 * (((cos_d * R(s.cos_eq)) * c_u) + (R(s.sin_eq) * sin_d)), R(0.0));
+  const R half_gam = R(0.5) * gam_s;
+  const R K_dif = half_gam * K_h;                            // :667
+  const R K_glob = (tau * K_h) + K_dif;                      // :634, :683
+  const R K_bs = (half_gam * albedo) * K_glob;               // :711
+  return ((tau * K_s) + K_dif) + K_bs;                       // :909
+}
+
+// One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
+// entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
+template <class P, bool VOL, class WindowFn>
+__device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
+                                          const CellStatic<typename P::raw>& s, Num<P> LC,
+                                          CellState<typename P::raw>& st, CellVol<typename P::raw>& vol,
+                                          Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
+                                          WindowFn&& window_sum, StepOut<typename P::raw>& o) {
+  using R = Num<P>;
+  const R dt(k.dt);
+  R h_snow(st.h_snow), h_swe(st.h_swe), h_ice(st.h_ice), h_iwe(st.h_iwe), Eccs(st.eccs), Ecci(st.ecci);
+
+  // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
+  const R T_K = T_air + 273.15;
+  R p0 = R(k.sea_p0) * nexp(R(s.a_elev) / (R(k.r_star) * T_K));
+  p0 = (p0 / 1000.0) * 10.0;
+  // ---- update_P_rain :585, update_P_snow :604  (P * bool)
+  const bool is_rain = T_air > R(s.t_rs);
+  const bool is_snow = T_air <= R(s.t_rs);
+  R P_rain, P_snow;
+  if constexpr (P::strict) {
+    P_rain = Pp * R(is_rain ? 1.0 : 0.0);
+    P_snow = Pp * R(is_snow ? 1.0 : 0.0);
+  } else {
+    P_rain = sel(is_rain, Pp, R(0.0));
+    P_snow = sel(is_snow, Pp, R(0.0));
+  }
+  if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
+    const R da(s.da_m2);
+    vol.vol_P = (R(vol.vol_P) + ((Pp * da) * dt)).v;
+    vol.P_max = nmax(R(vol.P_max), Pp).v;
+    vol.vol_PR = (R(vol.vol_PR) + ((P_rain * da) * dt)).v;
+    vol.vol_PS = (R(vol.vol_PS) + ((P_snow * da) * dt)).v;
+  }
+  // ---- vapour pressures :423-425
+  const R e_sat_air = e_sat_mbar<P>(k, T_air);
+  R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));     // :817
+  const R e_air = (e / 1000.0) * 10.0;                       // :818-821
+  const R RH = e_air / e_sat_air;                            // :838
+  // ---- update_dew_point :888-893
+  const R log_term = nlog(e_air / 6.1121);
+  const R T_dew = (R(257.14) * log_term) / (R(18.678) - log_term);
+  // ---- update_T_surf :906-911
+  const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
+  const R T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);
+  const R e_sat_surf = e_sat_mbar<P>(k, T_surf);
+  // ---- update_bulk_richardson_number :640-644
+  const R dT = T_air - T_surf;
+  const R top = R(k.gz) * dT;
+  R bot = (uz * uz) * T_K;
+  bot = sel(bot == 0.0, R(0.01), bot);
+  const R Ri = top / bot;
+  // ---- update_bulk_aero_conductance :670-733
+  const R arg = R(k.kappa) / nlog(nmax((R(k.z) - h_snow) / R(k.z0_air), R(0.01)));
+  const R Dn = uz * (arg * arg);
+  R Dh;
+  if (T_air == T_surf) Dh = Dn;
+  else if (Ri > 0.0) Dh = Dn / (R(1.0) + (R(10.0) * Ri));
+  else Dh = Dn * (R(1.0) - (R(10.0) * Ri));
+  // ---- update_sensible_heat_flux :744-745
+  const R Qh = (R(k.rho_cp_air) * Dh) * dT;
+  // ---- update_precipitable_water_content :919-920
+  const R W_p = R(1.12) * nexp(R(0.0614) * T_dew);
+  // ---- update_vapor_pressure(SURFACE=True) :853 ; update_latent_heat_flux :931-934
+  const R e_surf = RH * e_sat_surf;
+  const R Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
+  // ---- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471
+  const R solar_noon = (R(12.0) + LC) + R(tr.TE);
+  const R th = R(tr.clock_hour) - solar_noon;
+  // ---- update_albedo("aging") :1023-1059
+  const R r = sel(T_air > 0.0, R(0.12), R(0.05));
+  const R ring_new = (P_snow * dt) * R(k.ws_ratio);          // :1031-1033
+  const R tot = window_sum(ring_new);                        // :1027-1037
+  R n(st.n_days);
+  n = sel(tot >= 0.03, R(0.0), n);                           // :1040
+  n = sel(tot < 0.03, n + R(k.days_per_dt), n);              // :1041
+  R albedo(st.albedo);
+  if (h_snow > 0.0) albedo = R(0.4) + (R(0.44) * nexp((-n) * r));  // :1042-1048
+  if (h_snow == 0.0 && h_ice > 0.0) albedo = R(0.3);         // :1049-1053
+  if (h_snow == 0.0 && h_ice == 0.0) albedo = R(0.15);       // :1054-1058
+  // ---- update_net_shortwave_radiation :1122-1139
+  const R K_cs = clear_sky<P>(k, tr, s, th, W_p, albedo);
+  const R Qn_SW = K_cs * (R(1.0) - albedo);
+  // ---- update_em_air :1167-1192
+  R em_air;
+  if (!k.satterlund) {
+    const R x = (e_air / 10.0) / T_K;
+    const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
+    em_air = (term1 * R(k.emis_b)) + R(k.canopy);
+  } else {
+    em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, T_K / 2016.0)));
+  }
+  // ---- update_net_longwave_radiation :1231-1248
+  const R T_surf_K = T_surf + 273.15;
+  const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);
+  R LW_out = R(k.es_sigma) * npow4(T_surf_K);
+  LW_out = LW_out + (R(k.one_m_es) * LW_in);
+  const R Qn_LW = LW_in - LW_out;
+  // ---- update_net_energy_flux :1314  (Qa = Qc = 0, :312-313)
+  R Q_sum = ((Qn_SW + Qn_LW) + Qh) + Qe;
+  if constexpr (P::strict) Q_sum = (Q_sum + R(0.0)) + R(0.0);
+
+  // ---- snow: update_snow_meltrate :1364-1368, enforce_max_snow_meltrate :1465
+  const R previous_swe = h_swe;                              // :1571
+  const R E_in = Q_sum * dt;
+  R SM = (nmax(E_in - Eccs, R(0.0)) / dt) / R(k.rho_lf);
+  SM = nmax(SM, R(0.0));
+  if constexpr (VOL) vol.vol_SM = (R(vol.vol_SM) + (((SM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1486-1487
+  // ---- update_swe :1594-1606
+  h_swe = h_swe + (P_snow * dt);
+  SM = nmin(SM * 3600.0, h_swe) / 3600.0;
+  h_swe = h_swe - ((SM * dt) * 3600.0);
+  h_swe = nmax(h_swe, R(0.0));
+  // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
+  if (P_snow > 0.0) {
+    const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
+    const R T_wb = ((((T_air * natan(R(0.151977) * nsqrt(RH + 8.313659))) + natan(T_air + RH)) -
+                     natan(RH - 1.676331)) +
+                    ((R(0.00391838) * npow15(RH)) * natan(R(0.023101) * RH))) -
+                   4.86035;
+    const R del_T = R(k.T0) - T_wb;
+    Eccs = nmax((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in, R(0.0));
+  }
+  // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
+  R IM = nmax((nmax(E_in - Ecci, R(0.0)) / dt) / R(k.rho_lf), R(0.0));
+  IM = sel((h_swe == 0.0) && (previous_swe == 0.0), IM, R(0.0));
+  Ecci = nmax(Ecci - E_in, R(0.0));
+  Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
+  // ---- enforce_max_ice_meltrate :1473-1480
+  IM = nmax(nmin(IM, h_iwe / dt), R(0.0));
+  if constexpr (VOL) vol.vol_IM = (R(vol.vol_IM) + (((IM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1493-1494
+  // ---- update_iwe :1612-1617
+  IM = nmin(IM * 3600.0, h_iwe) / 3600.0;
+  h_iwe = h_iwe - ((IM * dt) * 3600.0);
+  h_iwe = nmax(h_iwe, R(0.0));
+  // ---- update_combined_meltrate :1441-1445
+  const R M_total = (IM + SM) + (P_rain / 3600.0);
+  // ---- update_snow_depth :1711, update_ice_depth :1726
+  h_snow = h_swe * R(k.ws_ratio);
+  h_ice = h_iwe * R(k.wi_ratio);
+  // ---- update_snowpack_cold_content :1552-1558
+  if (P_snow <= 0.0) Eccs = nmax(Eccs - E_in, R(0.0));
+  if (h_snow == 0.0) Eccs = R(0.0);
+
+  st.h_snow = h_snow.v; st.h_swe = h_swe.v; st.h_ice = h_ice.v; st.h_iwe = h_iwe.v;
+  st.eccs = Eccs.v; st.ecci = Ecci.v; st.albedo = albedo.v; st.n_days = n.v;
+  o.SM = SM.v; o.IM = IM.v; o.M_total = M_total.v; o.RH = RH.v;
+  o.p0 = p0.v; o.e_sat_air = e_sat_air.v; o.e_air = e_air.v; o.T_dew = T_dew.v; o.T_surf = T_surf.v;
+  o.e_sat_surf = e_sat_surf.v; o.Ri = Ri.v; o.Dn = Dn.v; o.Dh = Dh.v; o.Qh = Qh.v; o.W_p = W_p.v;
+  o.e_surf = e_surf.v; o.Qe = Qe.v; o.th = th.v; o.Qn_SW = Qn_SW.v; o.em_air = em_air.v; o.Qn_LW = Qn_LW.v;
+  o.Q_sum = Q_sum.v; o.P_rain = P_rain.v; o.P_snow = P_snow.v;
+}
+
+}  // namespace tfg

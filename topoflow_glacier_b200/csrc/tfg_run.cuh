@@ -1,0 +1,242 @@
+// tfg_run.cuh -- the fused, time-looping melt kernel (K1) and its launcher.
+//
+// One thread owns one cell for the whole launch: static tables and carried state are loaded once,
+// stay in registers for n_steps timesteps, and are written back once.  Per step a thread reads only
+// its five forcings (coalesced, [step][var][cell], streaming loads prefetched one step ahead) plus one
+// slot of the 3-day snowfall window.  This replaces the reference's per-step driver loop
+// (examples/run_topoflow_glacier.py:64-109) around BmiTopoflowGlacier.update()
+// (bmi_topoflow_glacier.py:413-465).
+#pragma once
+#include "tfg_physics.cuh"
+#include "../../include/tfglacier.h"
+
+namespace tfg {
+
+constexpr int kBlock = 128;
+
+template <class raw>
+struct RunParams {
+  int64_t n_cells, step0;
+  int32_t n_steps, ring_slots, n_tz, exact_ring;
+  const raw* forcing;
+  const raw *a_elev, *sin_lat, *cos_lat, *neg_tan_lat, *lon, *sin_eq, *cos_eq, *neg_tan_eq, *dlon, *t_noon, *da_m2,
+      *t_rs;
+  const int32_t* basin_id;
+  const uint8_t* tz_idx;
+  raw *h_snow, *h_swe, *h_ice, *h_iwe, *eccs, *ecci, *albedo, *n_days, *SM, *IM, *M_total, *RH;
+  raw *vol_P, *vol_PR, *vol_PS, *vol_SM, *vol_IM, *P_max;
+  raw* ring;
+  const TimeRow<raw>* rows;  // device, indexed by absolute step
+  const raw* gmt;            // device, [step][n_tz]
+  raw* record;
+  uint64_t record_mask;
+  int32_t n_rec;
+  double* basin_agg;
+  int32_t n_basin;
+  Consts<raw> k;
+};
+
+template <class raw> __device__ __forceinline__ raw ld_stream(const raw* p) { return __ldcs(p); }
+
+// np.sum over the window in logical order (oldest first), i.e. NumPy's pairwise kernel for n <= 128:
+// eight interleaved accumulators, then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder.
+// `newest` is the physical slot written this step; logical j lives in physical (newest+1+j) % slots.
+template <class P>
+__device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int64_t N, int slots, int newest) {
+  using R = Num<P>;
+  int p = newest + 1;
+  if (p >= slots) p -= slots;
+  auto next = [&]() {
+    R v(ring[(int64_t)p * N]);
+    if (++p >= slots) p = 0;
+    return v;
+  };
+  if (slots < 8) {
+    R res(0.0);
+    for (int i = 0; i < slots; ++i) res = res + next();
+    return res;
+  }
+  R r0 = next(), r1 = next(), r2 = next(), r3 = next(), r4 = next(), r5 = next(), r6 = next(), r7 = next();
+  int i = 8;
+  for (; i < slots - (slots % 8); i += 8) {
+    r0 = r0 + next(); r1 = r1 + next(); r2 = r2 + next(); r3 = r3 + next();
+    r4 = r4 + next(); r5 = r5 + next(); r6 = r6 + next(); r7 = r7 + next();
+  }
+  R res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  for (; i < slots; ++i) res = res + next();
+  return res;
+}
+
+template <class P, bool REC, bool AGG, bool VOL>
+__global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
+  using raw = typename P::raw;
+  using R = Num<P>;
+  const int64_t gid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool active = gid < p.n_cells;
+  const int64_t c = active ? gid : p.n_cells - 1;
+  const int64_t N = p.n_cells;
+
+  CellStatic<raw> s;
+  s.a_elev = __ldg(p.a_elev + c); s.sin_lat = __ldg(p.sin_lat + c); s.cos_lat = __ldg(p.cos_lat + c);
+  s.neg_tan_lat = __ldg(p.neg_tan_lat + c); s.sin_eq = __ldg(p.sin_eq + c); s.cos_eq = __ldg(p.cos_eq + c);
+  s.neg_tan_eq = __ldg(p.neg_tan_eq + c); s.dlon = __ldg(p.dlon + c); s.t_noon = __ldg(p.t_noon + c);
+  s.da_m2 = __ldg(p.da_m2 + c); s.t_rs = __ldg(p.t_rs + c);
+  const R lon(__ldg(p.lon + c));
+  const int tz = p.tz_idx ? (int)__ldg(p.tz_idx + c) : 0;
+
+  CellState<raw> st;
+  st.h_snow = p.h_snow[c]; st.h_swe = p.h_swe[c]; st.h_ice = p.h_ice[c]; st.h_iwe = p.h_iwe[c];
+  st.eccs = p.eccs[c]; st.ecci = p.ecci[c]; st.albedo = p.albedo[c]; st.n_days = p.n_days[c];
+  CellVol<raw> vol = {0, 0, 0, 0, 0, 0};
+  const bool have_vol = VOL && p.vol_P != nullptr;
+  if (have_vol) {
+    vol.vol_P = p.vol_P[c]; vol.vol_PR = p.vol_PR[c]; vol.vol_PS = p.vol_PS[c];
+    vol.vol_SM = p.vol_SM[c]; vol.vol_IM = p.vol_IM[c]; vol.P_max = p.P_max[c];
+  }
+
+  const int slots = p.ring_slots;
+  int slot = (int)(p.step0 % slots);
+  raw* ring = p.ring + c;
+  const bool exact = p.exact_ring != 0;
+  // incremental window sum: seeded from the stored window, re-derived exactly (reference summation
+  // order) whenever it comes within a guard band of the 0.03 m threshold of :1040
+  R tot(0.0);
+  if (!exact) {
+    for (int j = 0; j < slots; ++j) tot = tot + R(ring[(int64_t)j * N]);
+  }
+  R tot_hi = nabs(tot);
+  const R guard(P::f32 ? 1e-4 : 1e-9);
+
+  int basin = 0;
+  bool warp_uniform = false;
+  const bool have_agg = AGG && p.basin_agg != nullptr && p.basin_id != nullptr;
+  if (have_agg) {
+    basin = __ldg(p.basin_id + c);
+    warp_uniform = __all_sync(0xffffffffu, basin == __shfl_sync(0xffffffffu, basin, 0));
+  }
+
+  const raw* f = p.forcing + c;
+  raw f0 = ld_stream(f), f1 = ld_stream(f + N), f2 = ld_stream(f + 2 * N), f3 = ld_stream(f + 3 * N),
+      f4 = ld_stream(f + 4 * N);
+  raw r_old = ring[(int64_t)slot * N];
+  R LC(0.0);
+  raw gmt_prev = p.gmt[p.step0 * p.n_tz + tz];
+  LC = ((R(gmt_prev) * 15.0) - lon) / 15.0;  // True_Solar_Noon, solar_funcs.py:1466-1468
+
+  StepOut<raw> o;
+  for (int t = 0; t < p.n_steps; ++t) {
+    raw g0 = f0, g1 = f1, g2 = f2, g3 = f3, g4 = f4;
+    if (t + 1 < p.n_steps) {  // prefetch the next step's forcings
+      const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
+      g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
+      g4 = ld_stream(fn + 4 * N);
+    }
+    const int64_t step = p.step0 + t;
+    const TimeRow<raw> row = p.rows[step];
+    const raw gmt = p.gmt[step * p.n_tz + tz];
+    if (gmt != gmt_prev) {  // DST switch: piece-wise constant in time
+      gmt_prev = gmt;
+      LC = ((R(gmt) * 15.0) - lon) / 15.0;
+    }
+    const int slot_next = (slot + 1 == slots) ? 0 : slot + 1;
+    raw r_next = 0;
+    R tot_now;
+    auto window = [&](R ring_new) -> R {
+      if (active) ring[(int64_t)slot * N] = ring_new.v;  // np.roll(-1) + write of the newest slot, :1027-1033
+      if (exact) {
+        tot_now = window_sum_exact<P>(ring, N, slots, slot);
+      } else {
+        tot = (tot - R(r_old)) + ring_new;
+        tot_hi = nmax(tot_hi, nabs(tot));
+        if (nabs(tot - 0.03) <= guard * nmax(tot_hi, R(1.0))) {
+          tot = window_sum_exact<P>(ring, N, slots, slot);
+          tot_hi = nabs(tot);
+        }
+        tot_now = tot;
+      }
+      r_next = ring[(int64_t)slot_next * N];  // next step's oldest entry (after this step's store)
+      return tot_now;
+    };
+    cell_step<P, VOL>(p.k, row, s, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+
+    if constexpr (REC) {
+      if (active && p.record != nullptr) {
+        raw* rp = p.record + ((int64_t)t * p.n_rec) * N + c;
+        const uint64_t m = p.record_mask;
+        int r = 0;
+#define TFG_PUT(bit, val)              \
+  if ((m >> (bit)) & 1ull) {           \
+    rp[(int64_t)r * N] = (val);        \
+    ++r;                               \
+  }
+        TFG_PUT(TFG_REC_H_SNOW, st.h_snow) TFG_PUT(TFG_REC_H_SWE, st.h_swe) TFG_PUT(TFG_REC_SM, o.SM)
+        TFG_PUT(TFG_REC_H_ICE, st.h_ice) TFG_PUT(TFG_REC_H_IWE, st.h_iwe) TFG_PUT(TFG_REC_IM, o.IM)
+        TFG_PUT(TFG_REC_M_TOTAL, o.M_total) TFG_PUT(TFG_REC_RH, o.RH) TFG_PUT(TFG_REC_P0, o.p0)
+        TFG_PUT(TFG_REC_E_SAT_AIR, o.e_sat_air) TFG_PUT(TFG_REC_E_AIR, o.e_air) TFG_PUT(TFG_REC_T_DEW, o.T_dew)
+        TFG_PUT(TFG_REC_T_SURF, o.T_surf) TFG_PUT(TFG_REC_E_SAT_SURF, o.e_sat_surf) TFG_PUT(TFG_REC_RI, o.Ri)
+        TFG_PUT(TFG_REC_DN, o.Dn) TFG_PUT(TFG_REC_DH, o.Dh) TFG_PUT(TFG_REC_QH, o.Qh) TFG_PUT(TFG_REC_W_P, o.W_p)
+        TFG_PUT(TFG_REC_E_SURF, o.e_surf) TFG_PUT(TFG_REC_QE, o.Qe) TFG_PUT(TFG_REC_TSN_OFFSET, o.th)
+        TFG_PUT(TFG_REC_ALBEDO, st.albedo) TFG_PUT(TFG_REC_N_DAYS, st.n_days) TFG_PUT(TFG_REC_QN_SW, o.Qn_SW)
+        TFG_PUT(TFG_REC_EM_AIR, o.em_air) TFG_PUT(TFG_REC_QN_LW, o.Qn_LW) TFG_PUT(TFG_REC_Q_SUM, o.Q_sum)
+        TFG_PUT(TFG_REC_ECCS, st.eccs) TFG_PUT(TFG_REC_ECCI, st.ecci) TFG_PUT(TFG_REC_SNOW3DAY, tot_now.v)
+        TFG_PUT(TFG_REC_P_RAIN, o.P_rain) TFG_PUT(TFG_REC_P_SNOW, o.P_snow)
+#undef TFG_PUT
+      }
+    }
+    if constexpr (AGG) {
+      if (have_agg) {
+        // area-weighted basin sums (np.sum sites :567-568,:1486-1494 and the driver's `* da_m2`):
+        // warp-shuffle tree when the warp sits inside one basin, one RED per warp and quantity
+        const double da = (double)s.da_m2;
+        double v0 = active ? (double)o.M_total * da : 0.0;
+        double v1 = active ? (double)st.h_swe * da : 0.0;
+        double v2 = active ? (double)st.h_iwe * da : 0.0;
+        double* dst = p.basin_agg + ((int64_t)t * p.n_basin + basin) * TFG_N_AGG;
+        if (warp_uniform) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+          }
+          if ((threadIdx.x & 31) == 0) {
+            atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2);
+          }
+        } else if (active) {
+          atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2);
+        }
+      }
+    }
+    f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4;
+    r_old = r_next;
+    slot = slot_next;
+  }
+
+  if (active) {
+    p.h_snow[c] = st.h_snow; p.h_swe[c] = st.h_swe; p.h_ice[c] = st.h_ice; p.h_iwe[c] = st.h_iwe;
+    p.eccs[c] = st.eccs; p.ecci[c] = st.ecci; p.albedo[c] = st.albedo; p.n_days[c] = st.n_days;
+    p.SM[c] = o.SM; p.IM[c] = o.IM; p.M_total[c] = o.M_total; p.RH[c] = o.RH;
+    if (have_vol) {
+      p.vol_P[c] = vol.vol_P; p.vol_PR[c] = vol.vol_PR; p.vol_PS[c] = vol.vol_PS;
+      p.vol_SM[c] = vol.vol_SM; p.vol_IM[c] = vol.vol_IM; p.P_max[c] = vol.P_max;
+    }
+  }
+}
+
+// host-side dispatch over the compile-time switches; defined once per arithmetic mode (one TU each)
+template <class P>
+cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, bool vol, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((p.n_cells + kBlock - 1) / kBlock);
+  if (rec) run_kernel<P, true, true, true><<<grid, kBlock, 0, stream>>>(p);
+  else if (agg && vol) run_kernel<P, false, true, true><<<grid, kBlock, 0, stream>>>(p);
+  else if (agg) run_kernel<P, false, true, false><<<grid, kBlock, 0, stream>>>(p);
+  else if (vol) run_kernel<P, false, false, true><<<grid, kBlock, 0, stream>>>(p);
+  else run_kernel<P, false, false, false><<<grid, kBlock, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_run_strict(const RunParams<double>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
+cudaError_t launch_run_fast(const RunParams<double>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
+cudaError_t launch_run_f32(const RunParams<float>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
+
+}  // namespace tfg

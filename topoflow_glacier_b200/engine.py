@@ -1,0 +1,234 @@
+"""Device-resident ensemble of melt cells driven through the C ABI.
+
+``MeltEngine`` owns every per-cell array as a ``torch`` CUDA tensor (PyTorch is used for device memory and
+streams only), binds their raw pointers into a ``tfg_ctx`` and advances all cells with ``tfg_run``.  One
+engine = one shard of cells on one GPU.  It is the N-cell counterpart of what one reference instance keeps
+in ``Context`` (reference ``physics/context.py:18-71``) and in the attributes set up by
+``BmiTopoflowGlacier.initialize`` (reference ``bmi_topoflow_glacier.py:274-411``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Mapping, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+from .config import KERNEL_CONSTANTS
+from .statics import cell_tables
+from .timebase import parse_start, time_tables, utc_offsets
+
+__all__ = ["MeltEngine", "INPUT_ROWS", "STATE_ROWS"]
+
+# rows of the input block; the first five are the live forcings in kernel order (TFG_N_FORCING)
+INPUT_ROWS = ("P", "T_air", "P_air", "Hum_sp", "uz", "LW_in", "SW_in")
+# rows of the state block (order of tfg_state, minus the ring)
+STATE_ROWS = ("h_snow", "h_swe", "h_ice", "h_iwe", "Eccs", "Ecci", "albedo", "n", "SM", "IM", "M_total", "RH",
+              "vol_P", "vol_PR", "vol_PS", "vol_SM", "vol_IM", "P_max")
+_STATE_FIELD = dict(zip(STATE_ROWS, _lib.STATE_FIELDS))  # python name -> C field
+
+
+def _require_cuda(device: int) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("topoflow_glacier_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", device)
+
+
+class MeltEngine:
+    """All cells of one shard, resident in HBM.
+
+    Parameters
+    ----------
+    cells : mapping with float64 ``[N]`` arrays ``lat, lon, slope, aspect, elev, da, h0_snow, h0_ice, h0_swe,
+        h0_iwe, T_rain_snow`` (names of the yaml keys; ``da`` in km2)
+    consts : mapping holding the physical constants (``config.KERNEL_CONSTANTS`` keys, ``SATTERLUND``)
+    start_time : ``YYYYMMDDHH`` string; ``dt_hours`` : timestep [h]
+    zones : list of IANA names / fixed offsets; ``tz_idx`` : per-cell index into it (uint8) or None
+    basin_id : per-cell int32 basin index in ``[0, n_basin)`` or None
+    mode : ``"f64"`` (strict), ``"f64_fast"`` or ``"f32"``
+    horizon_steps : number of steps the host time tables are prepared for (extended on demand)
+    """
+
+    def __init__(self, cells: Mapping[str, np.ndarray], consts: Mapping[str, float], start_time, dt_hours: int = 1,
+                 zones: Sequence = ("America/Los_Angeles",), tz_idx: Optional[np.ndarray] = None,
+                 basin_id: Optional[np.ndarray] = None, n_basin: int = 0, mode: str = "f64", device: int = 0,
+                 horizon_steps: int = 24 * 366, diag_integrals: bool = True, device_statics: Optional[dict] = None):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.mode = _lib.MODE_NAMES[mode] if isinstance(mode, str) else int(mode)
+        self.dtype = torch.float32 if self.mode == _lib.F32 else torch.float64
+        self.dt_hours = dt_hours
+        self.start = parse_start(start_time) if not isinstance(start_time, pd.Timestamp) else start_time
+        self.zones = list(zones)
+        if not 1 <= len(self.zones) <= _lib.MAX_TZ:
+            raise ValueError(f"between 1 and {_lib.MAX_TZ} time zones per engine")
+        self.consts = {k: float(consts[k]) for k in KERNEL_CONSTANTS}
+        self.satterlund = bool(consts.get("SATTERLUND", False))
+        self.ring_slots = int(3 * 24 / dt_hours)
+        if not 1 <= self.ring_slots <= _lib.RING_SLOTS_MAX:
+            raise ValueError("dt must give between 1 and 72 snowfall-window slots")
+        self.step_index = 0
+        self.n_basin = int(n_basin)
+        self._keep = []  # host buffers that must outlive async copies
+
+        with torch.cuda.device(self.device):
+            ctx = C.c_void_p()
+            _lib.check(self.lib.tfg_create(C.byref(ctx), self.device.index, self.mode), "tfg_create")
+            self.ctx = ctx
+            self._set_constants()
+            if device_statics is not None:  # synthetic grids: tables already on the device
+                self.N = int(next(iter(device_statics.values())).numel())
+                self.static = {k: device_statics[k].to(self.device, self.dtype).contiguous() for k in _lib.STATIC_FIELDS}
+                init = {k: device_statics[k].to(self.device, self.dtype) for k in ("h0_snow", "h0_ice", "h0_swe", "h0_iwe")}
+            else:
+                tabs = cell_tables(cells["lat"], cells["lon"], cells["slope"], cells["aspect"], cells["elev"],
+                                   cells["da"], cells["T_rain_snow"], M_mass_air=self.consts["M_mass_air"],
+                                   g=self.consts["g"])
+                self.N = int(tabs["lon"].size)
+                self.static = {k: torch.as_tensor(tabs[k]).to(self.device, self.dtype).contiguous()
+                               for k in _lib.STATIC_FIELDS}
+                init = {k: torch.as_tensor(np.broadcast_to(np.asarray(cells[k], dtype=np.float64), (self.N,)).copy())
+                        .to(self.device, self.dtype) for k in ("h0_snow", "h0_ice", "h0_swe", "h0_iwe")}
+            N = self.N
+            if basin_id is None:
+                self.basin_id = None
+            elif torch.is_tensor(basin_id):
+                self.basin_id = basin_id.to(self.device, torch.int32).contiguous()
+            else:
+                self.basin_id = torch.as_tensor(np.ascontiguousarray(basin_id, dtype=np.int32)).to(self.device)
+            self.tz_idx = None if tz_idx is None else torch.as_tensor(
+                np.ascontiguousarray(tz_idx, dtype=np.uint8)).to(self.device)
+            self._bind_static()
+
+            self.inputs = torch.zeros(len(INPUT_ROWS), N, dtype=self.dtype, device=self.device)
+            self.state = torch.zeros(len(STATE_ROWS), N, dtype=self.dtype, device=self.device)
+            self.ring = torch.zeros(self.ring_slots, N, dtype=self.dtype, device=self.device)
+            self.diag_integrals = diag_integrals
+            self._init_state(init)
+            self._bind_state()
+            self._n_time = 0
+            self.ensure_horizon(horizon_steps)
+
+    # ---- binding -----------------------------------------------------------------------------------------
+    def _set_constants(self):
+        c = _lib.Constants()
+        for k, v in self.consts.items():
+            setattr(c, k, v)
+        c.dt_hours = float(self.dt_hours)
+        c.z_wind = 10.0  # reference bmi_topoflow_glacier.py:301
+        c.satterlund = int(self.satterlund)
+        c.ring_slots = self.ring_slots
+        _lib.check(self.lib.tfg_set_constants(self.ctx, C.byref(c)), "tfg_set_constants")
+
+    def _bind_static(self):
+        s = _lib.Statics()
+        for k in _lib.STATIC_FIELDS:
+            setattr(s, k, self.static[k].data_ptr())
+        s.basin_id = self.basin_id.data_ptr() if self.basin_id is not None else None
+        s.tz_idx = self.tz_idx.data_ptr() if self.tz_idx is not None else None
+        _lib.check(self.lib.tfg_bind_static(self.ctx, self.N, C.byref(s)), "tfg_bind_static")
+
+    def _init_state(self, init):
+        """Initial state of reference ``initialize()`` (``:350-395``): depths from the config, albedo 0.3,
+        cold contents ``max(rho*Cp*h*(T0 - T_surf), 0)`` with ``T_surf = 0``."""
+        c = self.consts
+        st = self.state
+        st.zero_()
+        self.row("h_snow").copy_(init["h0_snow"])
+        self.row("h_ice").copy_(init["h0_ice"])
+        self.row("h_swe").copy_(init["h0_swe"])
+        self.row("h_iwe").copy_(init["h0_iwe"])
+        self.row("albedo").fill_(0.3)
+        del_T = c["T0"] - 0.0
+        h_snow64 = init["h0_snow"].to(torch.float64)
+        self.row("Eccs").copy_(torch.clamp_min((c["rho_snow"] * c["Cp_snow"]) * h_snow64 * del_T, 0.0).to(self.dtype))
+        self.row("Ecci").fill_(max((c["rho_ice"] * c["Cp_ice"]) * c["h_active_layer"] * del_T, 0.0))
+        self.ring.zero_()
+
+    def _bind_state(self):
+        s = _lib.State()
+        for name in STATE_ROWS:
+            is_vol = name.startswith("vol_") or name == "P_max"
+            ptr = self.row(name).data_ptr() if (self.diag_integrals or not is_vol) else None
+            setattr(s, _STATE_FIELD[name], ptr)
+        s.ring = self.ring.data_ptr()
+        _lib.check(self.lib.tfg_bind_state(self.ctx, C.byref(s)), "tfg_bind_state")
+
+    def ensure_horizon(self, n_steps: int):
+        """Make sure host time tables cover absolute steps ``[0, n_steps)``."""
+        if n_steps <= self._n_time:
+            return
+        n = max(n_steps, 2 * self._n_time)
+        tt = time_tables(self.start, self.dt_hours, n)
+        rows = np.ascontiguousarray(np.stack([tt[k] for k in ("clock_hour", "TE", "sin_decl", "cos_decl", "tan_decl",
+                                                                "isc_e0")], axis=1), dtype=np.float64)
+        gmt = utc_offsets(tt["when"], self.zones)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.tfg_bind_time(self.ctx, rows.ctypes.data, gmt.ctypes.data, n, gmt.shape[1], stream),
+                   "tfg_bind_time")
+        self._n_time = n
+
+    # ---- access ------------------------------------------------------------------------------------------
+    def row(self, name: str) -> torch.Tensor:
+        """Live ``[N]`` tensor of an input or state variable (internal names)."""
+        if name in STATE_ROWS:
+            return self.state[STATE_ROWS.index(name)]
+        return self.inputs[INPUT_ROWS.index(name)]
+
+    @property
+    def stream_ptr(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- the hot path --------------------------------------------------------------------------------------
+    def run(self, forcing: torch.Tensor, n_steps: Optional[int] = None, record: Optional[Iterable[str]] = None,
+            basin_agg: Optional[torch.Tensor] = None):
+        """Advance every cell ``n_steps`` timesteps with ``forcing[T, 5, N]`` (device, engine dtype).
+
+        Returns ``{name: [T, N] tensor}`` for the recorded quantities (empty dict if none).  ``basin_agg``
+        (float64 ``[T, n_basin, 3]``) is accumulated into.
+        """
+        T = int(n_steps if n_steps is not None else forcing.shape[0])
+        if forcing.dtype != self.dtype or not forcing.is_cuda or not forcing.is_contiguous():
+            raise ValueError("forcing must be a contiguous device tensor of the engine dtype")
+        if forcing.numel() < T * _lib.N_FORCING * self.N:
+            raise ValueError("forcing block smaller than [n_steps, 5, N]")
+        self.ensure_horizon(self.step_index + T)
+        rec_t, mask, names = None, 0, []
+        if record:
+            names = sorted(set(record), key=lambda k: _lib.REC_BIT[k])
+            for k in names:
+                mask |= 1 << _lib.REC_BIT[k]
+            rec_t = torch.empty(T, len(names), self.N, dtype=self.dtype, device=self.device)
+        if basin_agg is not None:
+            if basin_agg.dtype != torch.float64 or basin_agg.numel() < T * self.n_basin * _lib.N_AGG:
+                raise ValueError("basin_agg must be float64 [n_steps, n_basin, 3]")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tfg_run(
+                self.ctx, forcing.data_ptr(), self.step_index, T, rec_t.data_ptr() if rec_t is not None else None,
+                mask, basin_agg.data_ptr() if basin_agg is not None else None, self.n_basin, self.stream_ptr),
+                "tfg_run")
+        self.step_index += T
+        return {k: rec_t[:, i] for i, k in enumerate(names)} if rec_t is not None else {}
+
+    def step(self, record: Optional[Iterable[str]] = None):
+        """One literal ``update()`` from the current input block."""
+        return self.run(self.inputs, 1, record=record)
+
+    def synth_forcing(self, out: torch.Tensor, step0: int, n_steps: int, elev: torch.Tensor, seed: int):
+        _lib.check(self.lib.tfg_synth_forcing(self.ctx, out.data_ptr(), step0, n_steps, self.N, elev.data_ptr(), seed,
+                                              self.stream_ptr), "tfg_synth_forcing")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.tfg_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
