@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- cell-timesteps/sec of the fused energy-balance + melt kernel on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode f64_fast|f64|f32] [--impl reference]
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d cfg 4): a synthetic 4096 x 4096 glacierised raster
+(16 777 216 cells) PER GPU, hourly forcing, advanced in chunks of ``--chunk`` (default 128) timesteps.
+One bench "step" = one launch of the fused kernel over one forcing chunk for every cell of the rank
+(+ the all-reduce of the per-basin aggregates when N > 1).  Weak scaling: per-GPU work is fixed.
+
+* ``value``      whole-job cell-steps/s with the forcing chunk resident in HBM (86 GB in float64: far larger than
+                 L2, so no flush is needed between launches);
+* ``roofline``   the melt kernel alone, CUDA events on the launching stream; algorithmic bytes = 5 live forcings x
+                 element size per cell-step (40 B float64 / 20 B float32), peak = MEASURED_PEAKS.json hbm_gbs;
+* ``e2e``        the same metric through the public API with HOST buffers: pinned raw met columns ->
+                 ForcingStreamer (cudaMemcpyAsync on a side stream + unit-conversion kernel) -> tfg_run ->
+                 device->host copy of the eight BMI outputs and the basin aggregates, all inside the timed region;
+* ``cpu_baseline``  the NumPy oracle (a port of the reference: kind "port") on all host cores, on a bounded
+                 sample of the same cells and forcing; the sample is also used to check the GPU result.
+
+``--impl reference`` times that CPU port alone (the reference itself is a pure-Python package whose build
+backend is not installable offline) and prints the line with "impl": "reference".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "cell_timesteps_per_sec"
+UNIT = "cell-steps/s"
+GRID_CELLS = 4096 * 4096
+N_BASIN = 4096
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def _oracle_worker(args):
+    import numpy as np
+
+    from oracle.np_ref import CellStatics, Constants, OracleModel
+
+    statics, forcing, start, reps = args
+    cells = CellStatics(**statics, tz=[-8.0])
+    model = OracleModel(cells, Constants(), start, strict_pow=False)
+    t0 = time.perf_counter()
+    out = None
+    for _ in range(reps):
+        for t in range(forcing.shape[0]):
+            out = model.step(*forcing[t])
+    dt = time.perf_counter() - t0
+    return dt, {k: np.array(out[k]) for k in ("M_total", "h_swe", "h_iwe", "RH")}
+
+
+def cpu_port_throughput(statics: dict, forcing, start: str, cores: int, reps: int = 1):
+    """All host cores, one oracle instance per core on its slice of the sample cells."""
+    import multiprocessing as mp
+
+    import numpy as np
+
+    n = statics["lat"].size
+    bounds = np.linspace(0, n, cores + 1).astype(int)
+    jobs = []
+    for i in range(cores):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi > lo:
+            jobs.append(({k: v[lo:hi] for k, v in statics.items()}, np.ascontiguousarray(forcing[:, :, lo:hi]), start, reps))
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        res = pool.map(_oracle_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    last = {k: np.concatenate([r[1][k] for r in res]) for k in res[0][1]}
+    return n * forcing.shape[0] * reps / busy, wall, last
+
+
+def synthetic_host_sample(n_cells: int, n_steps: int, seed: int = 4096):
+    """Host-only synthetic cells + forcing with the cfg-4 distributions (used when no GPU is involved)."""
+    import numpy as np
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    U = lambda lo, hi: rng.uniform(lo, hi, n_cells)  # noqa: E731
+    swe = U(0, 1.5)
+    iwe = U(0, 60) * (rng.uniform(size=n_cells) < 0.4)
+    statics = {"da": np.full(n_cells, 9e-4), "slope": U(0, 120), "aspect": U(0, 360), "lon": U(-122.1, -121.4),
+               "lat": U(46.5, 47.1), "elev": U(1200, 4300), "h0_snow": swe * 20.0, "h0_ice": iwe * (1000.0 / 917.0),
+               "h0_swe": swe, "h0_iwe": iwe, "T_rain_snow": np.zeros(n_cells)}
+    hours = np.arange(n_steps)[:, None]
+    T2D = (275.15 + 9 * np.sin(2 * np.pi * ((274 + hours // 24) % 365 - 105) / 365)
+           + 4 * np.sin(2 * np.pi * (hours % 24 - 15) / 24) + rng.normal(0, 2, (n_steps, n_cells))
+           - 6.5e-3 * (statics["elev"][None, :] - 2400.0))
+    PSFC = 88900 + rng.normal(0, 400, (n_steps, n_cells))
+    Tc = T2D - 273.15
+    esat = 611.0 * np.exp(17.3 * Tc / (Tc + 237.3))
+    q = np.clip(0.8 * (0.622 * esat / (PSFC - 0.378 * esat)) * rng.uniform(0.5, 1, (n_steps, n_cells)), 5e-4, 0.012)
+    rain = np.where(rng.uniform(size=(n_steps, n_cells)) < 0.12, rng.exponential(0.5, (n_steps, n_cells)), 0.0)
+    uz = 3.0 * np.hypot(rng.normal(size=(n_steps, n_cells)), rng.normal(size=(n_steps, n_cells)))
+    forcing = np.stack([rain * 1e-3, T2D - 273.15, PSFC, q, uz], axis=1)
+    return statics, np.ascontiguousarray(forcing)
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation of the path (NumPy port), all host cores, bounded sample per step."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_cells = min(args.cpu_cells or 131072 * cores, 1 << 21)
+    n_steps = args.cpu_steps
+    statics, forcing = synthetic_host_sample(n_cells, n_steps)
+    times = []
+    for i in range(args.warmup + args.steps):
+        thr, wall, _ = cpu_port_throughput(statics, forcing, "2012100100", cores)
+        if i >= args.warmup:
+            times.append((thr, wall))
+    cs = n_cells * n_steps
+    wall = sum(w for _, w in times)
+    value = cs * len(times) / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic glacierised raster (cfg-4 distributions), CPU sample", "cells": n_cells,
+                   "timesteps_per_step": n_steps},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_cells} cells x {n_steps} timesteps per step, oracle/np_ref.py, one process per core"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from topoflow_glacier_b200 import _lib
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.forcing import ForcingStreamer
+    from topoflow_glacier_b200.sharding import BasinAggregates
+    from topoflow_glacier_b200.synthetic import synthetic_cells
+    from topoflow_glacier_b200.config import default_constants
+
+    rank, local_rank, world = env_rank()
+    # ---- CPU baseline first (rank 0, N == 1), before CUDA is initialised so that fork() is safe ------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_cells or 131072 * cores, 1 << 21)
+        statics_h, forcing_h = synthetic_host_sample(ns, args.cpu_steps)
+        thr, wall_cpu, last = cpu_port_throughput(statics_h, forcing_h, "2012100100", cores)
+        cpu = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{ns} cells (cfg-4 distributions) x {args.cpu_steps} timesteps, oracle/np_ref.py, one process "
+                         f"per core ({wall_cpu:.1f} s wall)", "_sample": (statics_h, forcing_h, last)}
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the melt path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_cells, Tc, mode = args.cells, args.chunk, args.mode
+    es = 4 if mode == "f32" else 8
+    consts = default_constants()
+    tabs = synthetic_cells(n_cells, seed=4096 + rank, device=dev)
+    raw_attrs = tabs.pop("raw")
+    per_basin = -(-n_cells * world // N_BASIN)
+    basin_id = ((torch.arange(n_cells, device=dev, dtype=torch.int64) + rank * n_cells) // per_basin).to(torch.int32)
+    horizon = (args.warmup + args.steps + 4) * Tc + (args.e2e_steps + args.warmup + 2) * args.e2e_chunk + 64
+    eng = MeltEngine(None, consts, "2012100100", dt_hours=1, zones=[-8.0], basin_id=basin_id, n_basin=N_BASIN,
+                     mode=mode, device=local_rank, horizon_steps=horizon, device_statics=tabs)
+    elev = raw_attrs["elev"].to(eng.dtype)
+    forcing = torch.empty(Tc, 5, n_cells, dtype=eng.dtype, device=dev)
+    eng.synth_forcing(forcing, 0, Tc, elev, seed=20121001 + rank)
+    agg = BasinAggregates(Tc, N_BASIN, device=dev)
+    torch.cuda.synchronize()
+
+    # ---- GPU result on the CPU sample (same host-generated cells and forcing): the correctness check -----
+    if cpu is not None:
+        statics_h, forcing_h, last = cpu.pop("_sample")
+        nt = forcing_h.shape[0]
+        chk = MeltEngine(statics_h, consts, "2012100100", zones=[-8.0], mode=mode, device=local_rank,
+                         horizon_steps=nt + 1)
+        chk.run(torch.as_tensor(forcing_h).to(dev, chk.dtype).contiguous(), nt)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k in ("M_total", "h_swe", "h_iwe", "RH"):
+            g = chk.row(k).to(torch.float64).cpu().numpy()
+            worst = max(worst, float(np.max(np.abs(g - last[k]) / (np.abs(last[k]) + 1e-9))))
+        chk.close()
+        cpu["gpu_vs_cpu_max_rel_err_on_sample"] = worst
+
+    def one_step():
+        agg.zero()
+        eng.run(forcing, Tc, basin_agg=agg.buffer)
+        agg.reduce()
+
+    for _ in range(args.warmup):
+        one_step()
+    # ---- kernel-only timing (CUDA events around each launch, launching stream) -----------------------------
+    evs = []
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    start_all, end_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start_all.record()
+    for _ in range(args.steps):
+        agg.zero()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.run(forcing, Tc, basin_agg=agg.buffer)
+        b.record()
+        agg.reduce()
+        evs.append((a, b))
+    end_all.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = start_all.elapsed_time(end_all)
+    kern_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    cell_steps = n_cells * Tc
+    value = world * cell_steps * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers -----------------------------------------------
+    Te = args.e2e_chunk
+    raw_dtype = torch.float32 if args.e2e_raw == "float32" else torch.float64
+    raw_host = torch.empty(Te, 6, n_cells, dtype=raw_dtype).pin_memory()
+    # raw met columns derived from the synthetic chunk (mm/h, K, Pa, kg/kg, U, V)
+    blk = forcing[:Te].to(torch.float64)
+    raw_dev = torch.stack([blk[:, 0] * 1e3, blk[:, 1] + 273.15, blk[:, 2], blk[:, 3], blk[:, 4] * 0.6, blk[:, 4] * 0.8],
+                          dim=1).to(raw_dtype)
+    raw_host.copy_(raw_dev)
+    del raw_dev, blk
+    streamer = ForcingStreamer(eng, Te, raw_dtype=args.e2e_raw)
+    out_host = torch.empty(8, n_cells, dtype=eng.dtype).pin_memory()
+    agg_e = BasinAggregates(Te, N_BASIN, device=dev)
+    agg_host = torch.empty(Te, N_BASIN, 3, dtype=torch.float64).pin_memory()
+    out_rows = torch.tensor([0, 1, 8, 2, 3, 9, 10, 11], device=dev)  # h_snow,h_swe,SM,h_ice,h_iwe,IM,M_total,RH
+
+    def e2e_step():
+        for chunk in streamer.chunks(raw_host):
+            agg_e.zero()
+            eng.run(chunk, chunk.shape[0], basin_agg=agg_e.buffer)
+            agg_e.reduce()
+        out_host.copy_(eng.state.index_select(0, out_rows), non_blocking=True)
+        agg_host.copy_(agg_e.buffer, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_cells * Te * args.e2e_steps / float(t.item())
+    h2d = raw_host.numel() * raw_host.element_size()
+    d2h = out_host.numel() * out_host.element_size() + agg_host.numel() * 8
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = es * _lib.N_FORCING * cell_steps / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(f"{mode}:{n_cells}x{Tc}")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if mode == "f32" else "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 4096x4096 glacierised raster per GPU (BASELINE configs[3]), hourly forcing",
+                       "cells_per_gpu": n_cells, "timesteps_per_step": Tc, "arithmetic_mode": mode,
+                       "basin_aggregates": N_BASIN, "forcing": "device-resident chunk, Philox synthetic, reused each step",
+                       "l2": f"inputs {es * 5 * cell_steps / 1e9:.1f} GB per launch >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"cells sharded x{world}, all_reduce of basin aggregates"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "tfg::run_kernel",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_cell_step": es * _lib.N_FORCING,
+                         "note": "FP64-pipe bound, not HBM bound: see profiles/ and DESIGN.md"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timesteps_per_step": Te, "raw_dtype": args.e2e_raw,
+                    "path": "pinned host raw met -> ForcingStreamer (tfg_ingest_async + tfg_convert_forcing) -> tfg_run "
+                            "-> D2H of 8 BMI outputs + basin aggregates"},
+            "gpu_launches": args.steps, "clocks": clocks, "wall_s": wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="f64_fast", choices=["f64", "f64_fast", "f32"])
+    ap.add_argument("--cells", type=int, default=GRID_CELLS)
+    ap.add_argument("--chunk", type=int, default=128, help="timesteps per launch")
+    ap.add_argument("--e2e-chunk", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-raw", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--cpu-cells", type=int, default=0)
+    ap.add_argument("--cpu-steps", type=int, default=24)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    return run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -154,10 +154,12 @@ TFG_API int tfg_run(tfg_ctx* ctx, const void* forcing, int64_t step0, int32_t n_
 TFG_API int tfg_ingest_async(tfg_ctx* ctx, const void* pinned_src, void* dev_dst, size_t bytes, void* stream,
                      void* done_event);
 /* raw met columns -> live forcings, on the device:
- *   raw dev [n_steps][6][n_cells] float64: RAINRATE [mm/h], T2D [K], PSFC [Pa], Q2D, U2D, V2D
+ *   raw dev [n_steps][6][n_cells] float64 (raw_elem_size 8) or float32 (4; widened exactly, e.g. AORC/NWM
+ *       single-precision sources): RAINRATE [mm/h], T2D [K], PSFC [Pa], Q2D, U2D, V2D
  *   out dev [n_steps][5][n_cells] (context element type):
  *   P = RAINRATE*1e-3, T_air = -273.15 + T2D, P_air, Hum_sp, uz = sqrt(U2D^2 + V2D^2)             */
-TFG_API int tfg_convert_forcing(tfg_ctx* ctx, const double* raw, void* out, int64_t n_steps, int64_t n_cells, void* stream);
+TFG_API int tfg_convert_forcing(tfg_ctx* ctx, const void* raw, int raw_elem_size, void* out, int64_t n_steps,
+                                int64_t n_cells, void* stream);
 /* wait (device-side) on `stream` for an event recorded by tfg_ingest_async on another stream     */
 TFG_API int tfg_stream_wait_event(tfg_ctx* ctx, void* stream, void* event);
 

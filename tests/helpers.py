@@ -15,7 +15,7 @@ CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "year4
 RTOL = 1e-12
 ATOL = {
     "p0": 0, "e_sat_air": 0, "e_air": 0, "RH": 0, "e_sat_surf": 0, "W_p": 0, "Dn": 0, "em_air": 0, "albedo": 0,
-    "n": 0, "snow3day": 1e-18, "P_rain": 0, "P_snow": 0, "TSN_offset": 1e-14,
+    "n": 0, "snow3day": 1e-13, "P_rain": 0, "P_snow": 0, "TSN_offset": 1e-14,
     "T_dew": 1e-12, "T_surf": 1e-12, "Ri": 1e-13, "Dh": 1e-15, "e_surf": 0,
     "Qh": 1e-10, "Qe": 1e-10, "Qn_SW": 1e-10, "Qn_LW": 1e-10, "Q_sum": 1e-9,
     "SM": 3e-18, "IM": 3e-18, "M_total": 3e-18,
@@ -47,9 +47,9 @@ def make_oracle(case: dict, strict_pow: bool = False, consts: dict | None = None
 
 
 def default_constants() -> dict:
-    from topoflow_glacier_b200.config import _TABLE
+    from topoflow_glacier_b200.config import default_constants as dc
 
-    return {k: v[1] for k, v in _TABLE.items() if v[1] is not ...}
+    return dc()
 
 
 def make_engine(case: dict, mode: str = "f64", **kw):

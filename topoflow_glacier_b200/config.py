@@ -16,7 +16,7 @@ from typing import Any, Optional
 
 from pydantic import ConfigDict, Field, create_model, field_validator
 
-__all__ = ["TopoflowGlacierConfig", "KERNEL_CONSTANTS"]
+__all__ = ["TopoflowGlacierConfig", "KERNEL_CONSTANTS", "default_constants"]
 
 _REQ = ...  # pydantic's "required" marker
 
@@ -102,3 +102,8 @@ TopoflowGlacierConfig = create_model(
     **{name: (tp, Field(default, description=desc, **cons)) for name, (tp, default, cons, desc) in _TABLE.items()},
 )
 TopoflowGlacierConfig.__doc__ = "Validates a topoflow-glacier catchment configuration."
+
+
+def default_constants() -> dict:
+    """Every defaulted field of the schema as a plain dict (the physical constants of a stock run)."""
+    return {k: v[1] for k, v in _TABLE.items() if v[1] is not _REQ}

@@ -129,13 +129,15 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
 }
 
 // ---- K2: raw met columns -> live forcings (examples/run_topoflow_glacier.py:40-73) -------------------
-template <class raw>
-__global__ void convert_kernel(const double* __restrict__ in, raw* __restrict__ out, int64_t n_steps, int64_t N) {
+template <class src_t, class raw>
+__global__ void convert_kernel(const src_t* __restrict__ in, raw* __restrict__ out, int64_t n_steps, int64_t N) {
   const int64_t total = n_steps * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = i / N, c = i - t * N;
-    const double* r = in + t * 6 * N + c;
-    const double rain = r[0], t2d = r[N], psfc = r[2 * N], q2d = r[3 * N], u = r[4 * N], v = r[5 * N];
+    const src_t* r = in + t * 6 * N + c;
+    // float32 sources (AORC / NWM style met data) widen exactly; arithmetic is float64 as in the driver
+    const double rain = (double)__ldcs(r), t2d = (double)__ldcs(r + N), psfc = (double)__ldcs(r + 2 * N),
+                 q2d = (double)__ldcs(r + 3 * N), u = (double)__ldcs(r + 4 * N), v = (double)__ldcs(r + 5 * N);
     raw* o = out + t * TFG_N_FORCING * N + c;
     o[0] = (raw)__dmul_rn(rain, 0.001);                         // precip * 10**(-3)
     o[N] = (raw)__dadd_rn(-273.15, t2d);                        // K_to_C + T2D
@@ -345,15 +347,25 @@ int tfg_stream_wait_event(tfg_ctx* x, void* stream, void* event) {
   return 0;
 }
 
-int tfg_convert_forcing(tfg_ctx* x, const double* raw, void* out, int64_t n_steps, int64_t n_cells, void* stream) {
+int tfg_convert_forcing(tfg_ctx* x, const void* raw, int raw_elem_size, void* out, int64_t n_steps, int64_t n_cells,
+                        void* stream) {
   if (!x || !raw || !out) return fail("tfg_convert_forcing: NULL argument");
   if (n_steps <= 0 || n_cells <= 0) return fail("tfg_convert_forcing: empty block");
+  if (raw_elem_size != 4 && raw_elem_size != 8) return fail("tfg_convert_forcing: raw_elem_size must be 4 or 8");
   TFG_CUDA(cudaSetDevice(x->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t total = n_steps * n_cells;
-  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  if (x->mode == TFG_F32) convert_kernel<float><<<grid, 256, 0, s>>>(raw, static_cast<float*>(out), n_steps, n_cells);
-  else convert_kernel<double><<<grid, 256, 0, s>>>(raw, static_cast<double*>(out), n_steps, n_cells);
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  const bool f32out = x->mode == TFG_F32;
+  if (raw_elem_size == 8) {
+    const double* r = static_cast<const double*>(raw);
+    if (f32out) convert_kernel<double, float><<<grid, 256, 0, s>>>(r, static_cast<float*>(out), n_steps, n_cells);
+    else convert_kernel<double, double><<<grid, 256, 0, s>>>(r, static_cast<double*>(out), n_steps, n_cells);
+  } else {
+    const float* r = static_cast<const float*>(raw);
+    if (f32out) convert_kernel<float, float><<<grid, 256, 0, s>>>(r, static_cast<float*>(out), n_steps, n_cells);
+    else convert_kernel<float, double><<<grid, 256, 0, s>>>(r, static_cast<double*>(out), n_steps, n_cells);
+  }
   TFG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -77,6 +77,22 @@ template <class P> __device__ __forceinline__ Num<P> nabs(Num<P> a) {
   if constexpr (P::f32) return Num<P>(fabsf(a.v)); else return Num<P>(fabs(a.v));
 }
 
+// ---- single-rounding operations that no mode may contract or reassociate ----------------------------
+// Used where the reference's exact rounding decides a discrete outcome (SWE/IWE reaching exactly 0,
+// the 0.03 m snowfall threshold): an FMA there changes which cells are snow-free.
+template <class P> __device__ __forceinline__ Num<P> xadd(Num<P> a, Num<P> b) {
+  if constexpr (P::f32) return Num<P>(__fadd_rn(a.v, b.v)); else return Num<P>(__dadd_rn(a.v, b.v));
+}
+template <class P> __device__ __forceinline__ Num<P> xsub(Num<P> a, Num<P> b) {
+  if constexpr (P::f32) return Num<P>(__fsub_rn(a.v, b.v)); else return Num<P>(__dsub_rn(a.v, b.v));
+}
+template <class P> __device__ __forceinline__ Num<P> xmul(Num<P> a, Num<P> b) {
+  if constexpr (P::f32) return Num<P>(__fmul_rn(a.v, b.v)); else return Num<P>(__dmul_rn(a.v, b.v));
+}
+template <class P> __device__ __forceinline__ Num<P> xdiv(Num<P> a, Num<P> b) {
+  if constexpr (P::f32) return Num<P>(__fdiv_rn(a.v, b.v)); else return Num<P>(__ddiv_rn(a.v, b.v));
+}
+
 // ---- transcendental functions ----------------------------------------------------------------------
 template <class P> __device__ __forceinline__ Num<P> nsqrt(Num<P> a) {
   if constexpr (P::strict) return Num<P>(__dsqrt_rn(a.v));

@@ -215,7 +215,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R th = R(tr.clock_hour) - solar_noon;
   // ---- update_albedo("aging") :1023-1059
   const R r = sel(T_air > 0.0, R(0.12), R(0.05));
-  const R ring_new = (P_snow * dt) * R(k.ws_ratio);          // :1031-1033
+  const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
   const R tot = window_sum(ring_new);                        // :1027-1037
   R n(st.n_days);
   n = sel(tot >= 0.03, R(0.0), n);                           // :1040
@@ -252,10 +252,11 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   R SM = (nmax(E_in - Eccs, R(0.0)) / dt) / R(k.rho_lf);
   SM = nmax(SM, R(0.0));
   if constexpr (VOL) vol.vol_SM = (R(vol.vol_SM) + (((SM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1486-1487
-  // ---- update_swe :1594-1606
-  h_swe = h_swe + (P_snow * dt);
-  SM = nmin(SM * 3600.0, h_swe) / 3600.0;
-  h_swe = h_swe - ((SM * dt) * 3600.0);
+  // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
+  const R k3600(3600.0);
+  h_swe = xadd(h_swe, xmul(P_snow, dt));
+  SM = xdiv(nmin(xmul(SM, k3600), h_swe), k3600);
+  h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
   h_swe = nmax(h_swe, R(0.0));
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
   if (P_snow > 0.0) {
@@ -275,15 +276,15 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- enforce_max_ice_meltrate :1473-1480
   IM = nmax(nmin(IM, h_iwe / dt), R(0.0));
   if constexpr (VOL) vol.vol_IM = (R(vol.vol_IM) + (((IM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1493-1494
-  // ---- update_iwe :1612-1617
-  IM = nmin(IM * 3600.0, h_iwe) / 3600.0;
-  h_iwe = h_iwe - ((IM * dt) * 3600.0);
+  // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
+  IM = xdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
+  h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
   h_iwe = nmax(h_iwe, R(0.0));
   // ---- update_combined_meltrate :1441-1445
   const R M_total = (IM + SM) + (P_rain / 3600.0);
   // ---- update_snow_depth :1711, update_ice_depth :1726
-  h_snow = h_swe * R(k.ws_ratio);
-  h_ice = h_iwe * R(k.wi_ratio);
+  h_snow = xmul(h_swe, R(k.ws_ratio));
+  h_ice = xmul(h_iwe, R(k.wi_ratio));
   // ---- update_snowpack_cold_content :1552-1558
   if (P_snow <= 0.0) Eccs = nmax(Eccs - E_in, R(0.0));
   if (h_snow == 0.0) Eccs = R(0.0);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ Run
   // order) whenever it comes within a guard band of the 0.03 m threshold of :1040
   R tot(0.0);
   if (!exact) {
-    for (int j = 0; j < slots; ++j) tot = tot + R(ring[(int64_t)j * N]);
+    for (int j = 0; j < slots; ++j) tot = xadd(tot, R(ring[(int64_t)j * N]));
   }
   R tot_hi = nabs(tot);
   const R guard(P::f32 ? 1e-4 : 1e-9);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ Run
       if (exact) {
         tot_now = window_sum_exact<P>(ring, N, slots, slot);
       } else {
-        tot = (tot - R(r_old)) + ring_new;
+        tot = xadd(xsub(tot, R(r_old)), ring_new);
         tot_hi = nmax(tot_hi, nabs(tot));
         if (nabs(tot - 0.03) <= guard * nmax(tot_hi, R(1.0))) {
           tot = window_sum_exact<P>(ring, N, slots, slot);

@@ -1,0 +1,142 @@
+"""Forcing ingestion: per-catchment met series -> pinned host blocks -> SoA device chunks.
+
+In the reference the driver script owns this step: it reads one CSV per catchment, converts units and
+calls ``set_value`` seven times per timestep (reference ``examples/run_topoflow_glacier.py:30-73``,
+``tests/integration_test.py:81-116``).  Here whole blocks of timesteps move at once:
+
+    CSV (header-keyed)  ->  raw block [T, 6, N] in pinned memory
+                        ->  cudaMemcpyAsync on a side stream            (tfg_ingest_async)
+                        ->  unit conversion into [T, 5, N] on the device  (tfg_convert_forcing)
+                        ->  event hand-off to the compute stream          (tfg_run consumes it)
+
+with two buffers so that the copy of chunk k+1 overlaps the melt kernel of chunk k.
+Only five of the seven BMI inputs are live (SW_in / LW_in are never read by the reference physics,
+``bmi_topoflow_glacier.py:1122-1139``, ``:1234-1235``), so only the columns they derive from are moved.
+"""
+
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Iterator, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+__all__ = ["RAW_COLUMNS", "read_forcing_csv", "stack_catchments", "convert_on_host", "ForcingStreamer"]
+
+# raw met columns moved to the device, in kernel order (tfg_convert_forcing)
+RAW_COLUMNS = ("RAINRATE", "T2D", "PSFC", "Q2D", "U2D", "V2D")
+
+
+def read_forcing_csv(path, start: Optional[pd.Timestamp] = None, end: Optional[pd.Timestamp] = None) -> np.ndarray:
+    """``[T, 6]`` float64 raw columns of one catchment, rows with ``start <= Time <= end``.
+
+    Columns are located by header name: the reference's two sample files order them differently
+    (``tests/data/sample-cat-3062920.csv:1`` vs ``tests/conftest.py:10``).
+    """
+    df = pd.read_csv(Path(path))
+    missing = [c for c in ("Time",) + RAW_COLUMNS if c not in df.columns]
+    if missing:
+        raise KeyError(f"{path}: missing forcing columns {missing}")
+    when = pd.to_datetime(df["Time"])
+    keep = np.ones(len(df), dtype=bool)
+    if start is not None:
+        keep &= (when >= start).values
+    if end is not None:
+        keep &= (when <= end).values
+    return np.ascontiguousarray(df.loc[keep, list(RAW_COLUMNS)].to_numpy(dtype=np.float64))
+
+
+def stack_catchments(series: Sequence[np.ndarray]) -> np.ndarray:
+    """``N`` arrays ``[T, 6]`` -> one block ``[T, 6, N]`` (cell index fastest), truncated to the shortest."""
+    T = min(s.shape[0] for s in series)
+    return np.ascontiguousarray(np.stack([s[:T] for s in series], axis=2))
+
+
+def convert_on_host(raw: np.ndarray) -> np.ndarray:
+    """Host statement of the unit conversions (``[T, 6, N]`` -> ``[T, 5, N]``); the device kernel must equal it.
+
+    ``P = RAINRATE * 10**-3`` [m/h], ``T_air = -273.15 + T2D`` [degC], ``uz = (U2D**2 + V2D**2) ** 0.5``
+    (``examples/run_topoflow_glacier.py:47-49,66-73``).
+    """
+    rain, t2d, psfc, q2d, u, v = (raw[:, i] for i in range(6))
+    return np.ascontiguousarray(np.stack([rain * 10 ** (-3), -273.15 + t2d, psfc, q2d, (u**2 + v**2) ** 0.5], axis=1))
+
+
+class ForcingStreamer:
+    """Double-buffered host -> device forcing pipeline for one ``MeltEngine``."""
+
+    def __init__(self, engine, chunk_steps: int, n_buffers: int = 2, raw_dtype="float64"):
+        import torch
+
+        from . import _lib
+
+        self.torch, self._lib = torch, _lib
+        self.e = engine
+        self.Tc = int(chunk_steps)
+        self.nb = int(n_buffers)
+        N, dev = engine.N, engine.device
+        self.side = torch.cuda.Stream(device=dev)
+        self.raw_dtype = torch.float32 if str(raw_dtype).endswith("32") else torch.float64
+        self.raw_es = 4 if self.raw_dtype == torch.float32 else 8
+        self.pinned = [None] * self.nb  # staging for NumPy sources, allocated on first use
+        self.d_raw = [torch.empty(self.Tc, 6, N, dtype=self.raw_dtype, device=dev) for _ in range(self.nb)]
+        self.d_out = [torch.empty(self.Tc, 5, N, dtype=engine.dtype, device=dev) for _ in range(self.nb)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(self.nb)]
+        self.ready = [torch.cuda.Event() for _ in range(self.nb)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.nb)]
+        self.h2d_bytes = 0
+
+    def _submit(self, b: int, block) -> int:
+        """Stage ``block`` ([Tk, 6, N] host) in buffer ``b``: (pinned copy,) async H2D, device conversion.
+
+        A ``torch`` tensor that already lives in pinned memory is copied from where it is; a NumPy
+        array is first staged in this streamer's own pinned buffer.
+        """
+        torch, lib, e = self.torch, self.e.lib, self.e
+        Tk = block.shape[0]
+        if torch.is_tensor(block) and block.is_pinned() and block.is_contiguous() and block.dtype == self.raw_dtype:
+            src_ptr = block.data_ptr()
+            self._keepalive = block
+        else:
+            if self.pinned[b] is None:
+                self.pinned[b] = torch.empty(self.Tc, 6, e.N, dtype=self.raw_dtype).pin_memory()
+            self.h2d_done[b].synchronize()  # pinned buffer free again
+            self.pinned[b][:Tk].numpy()[...] = block.numpy() if torch.is_tensor(block) else block
+            src_ptr = self.pinned[b].data_ptr()
+        self.side.wait_event(self.consumed[b])  # device buffers free again
+        nbytes = Tk * 6 * e.N * self.raw_es
+        with torch.cuda.device(e.device):
+            self._lib.check(lib.tfg_ingest_async(e.ctx, src_ptr, self.d_raw[b].data_ptr(), nbytes,
+                                                 self.side.cuda_stream, None), "tfg_ingest_async")
+            self.h2d_done[b].record(self.side)
+            self._lib.check(lib.tfg_convert_forcing(e.ctx, self.d_raw[b].data_ptr(), self.raw_es, self.d_out[b].data_ptr(), Tk, e.N,
+                                                    self.side.cuda_stream), "tfg_convert_forcing")
+            self.ready[b].record(self.side)
+        self.h2d_bytes += nbytes
+        return Tk
+
+    def chunks(self, raw) -> Iterator:
+        """Yield device forcing chunks ``[Tk, 5, N]`` in order; the consumer must launch its kernel on the
+        current stream before asking for the next chunk."""
+        torch = self.torch
+        T = raw.shape[0]
+        starts = list(range(0, T, self.Tc))
+        if not starts:
+            return
+        sizes = {}
+        sizes[0] = self._submit(0, raw[0:self.Tc])
+        for k, s in enumerate(starts):
+            b = k % self.nb
+            if k + 1 < len(starts):  # prefetch the next chunk while this one computes
+                nb = (k + 1) % self.nb
+                sizes[k + 1] = self._submit(nb, raw[starts[k + 1]:starts[k + 1] + self.Tc])
+            cur = torch.cuda.current_stream(self.e.device)
+            cur.wait_event(self.ready[b])
+            yield self.d_out[b][:sizes[k]]
+            self.consumed[b].record(cur)
+
+    def drive(self, raw: np.ndarray, **run_kw) -> None:
+        """Stream ``raw`` ([T, 6, N] host) through the engine."""
+        for chunk in self.chunks(raw):
+            self.e.run(chunk, chunk.shape[0], **run_kw)
