@@ -83,6 +83,8 @@ typedef struct tfg_time_row {
   double TE;         /* equation of time [h]                                                     */
   double sin_decl, cos_decl, tan_decl;
   double isc_e0;     /* I_sc * E0                                                                */
+  double cos_hour, sin_hour; /* cos/sin of omega*((clock_hour - 12) - TE), omega = 15 deg/h; read by the
+                              * fast modes only (angle-addition form of cos(omega*th))       */
 } tfg_time_row;
 
 /* Cell-only tables: replaces set_aspect_angle/set_slope_angle (bmi_topoflow_glacier.py:1082-1113),

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from topoflow_glacier_b200 import _lib
 
-    assert ctypes.sizeof(_lib.TimeRow) == 6 * 8
+    assert ctypes.sizeof(_lib.TimeRow) == 8 * 8
     assert ctypes.sizeof(_lib.Constants) == 26 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.Statics) == 14 * 8
     assert ctypes.sizeof(_lib.State) == 19 * 8

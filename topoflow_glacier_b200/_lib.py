@@ -34,7 +34,8 @@ class Constants(C.Structure):
 
 
 class TimeRow(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("clock_hour", "TE", "sin_decl", "cos_decl", "tan_decl", "isc_e0")]
+    _fields_ = [(n, C.c_double) for n in ("clock_hour", "TE", "sin_decl", "cos_decl", "tan_decl", "isc_e0",
+                                              "cos_hour", "sin_hour")]
 
 
 STATIC_FIELDS = ("a_elev", "sin_lat", "cos_lat", "neg_tan_lat", "lon", "sin_lat_eq", "cos_lat_eq", "neg_tan_lat_eq",
@@ -74,7 +75,9 @@ PROTOTYPES = {
                                     C.c_void_p]),
 }
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtfglacier.so"
+import os
+
+LIB_PATH = Path(os.environ.get("TFG_LIBRARY") or Path(__file__).resolve().parent / "lib" / "libtfglacier.so")
 _lib = None
 
 

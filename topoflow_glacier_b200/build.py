@@ -49,18 +49,23 @@ def is_current() -> bool:
     return LIB.exists() and stamp.exists() and stamp.read_text().strip() == source_digest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link libtfglacier.so; returns its path."""
-    if not force and is_current():
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """Compile every CUDA source for sm_100a and link libtfglacier.so; returns its path.
+
+    ``defines`` / ``out`` build an experimental variant next to the stock library (tuning sweeps).
+    """
+    variant = bool(defines) or out is not None
+    if not force and not variant and is_current():
         return LIB
     nvcc = _nvcc()
     LIBDIR.mkdir(exist_ok=True)
-    objdir = LIBDIR / "obj"
+    target = Path(out) if out else LIB
+    objdir = LIBDIR / ("obj_" + target.stem if variant else "obj")
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src: str) -> Path:
         obj = objdir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,13 +77,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(target), *map(str, objs)]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    (LIBDIR / "build.sha256").write_text(source_digest() + "\n")
-    return LIB
+    if not variant:
+        (LIBDIR / "build.sha256").write_text(source_digest() + "\n")
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -81,13 +81,16 @@ tfg::Consts<raw> derive(const tfg_constants& c) {
   k.omega = (360.0 / 24.0) * (pi / 180.0);
   k.rad2deg = 180.0 / pi;
   k.deg2rad = pi / 180.0;
+  k.inv_z0 = 1.0 / c.z0_air;
+  k.inv_dt = 1.0 / c.dt_hours;
+  k.inv_rho_lf = 1.0 / k.rho_lf;
   k.satterlund = c.satterlund;
   tfg::Consts<raw> r;
 #define CP(f) r.f = static_cast<raw>(k.f)
   CP(dt); CP(days_per_dt); CP(T0); CP(sea_p0); CP(r_star); CP(eps); CP(one_m_eps); CP(gz); CP(z); CP(z0_air);
   CP(kappa); CP(rho_cp_air); CP(rho_lv_air); CP(lhc); CP(ws_ratio); CP(wi_ratio); CP(rho_cp_snow); CP(rho_lf);
   CP(dust); CP(emis_a); CP(emis_b); CP(canopy); CP(sigma); CP(es_sigma); CP(one_m_es); CP(one_seventh); CP(omega);
-  CP(rad2deg); CP(deg2rad);
+  CP(rad2deg); CP(deg2rad); CP(inv_z0); CP(inv_dt); CP(inv_rho_lf);
 #undef CP
   r.satterlund = k.satterlund;
   return r;
@@ -277,20 +280,20 @@ int tfg_bind_time(tfg_ctx* x, const tfg_time_row* rows, const double* gmt, int64
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t es = tfg_elem_size(x);
   void *d_rows = nullptr, *d_gmt = nullptr;
-  TFG_CUDA(cudaMalloc(&d_rows, (size_t)n_steps * 6 * es));
+  TFG_CUDA(cudaMalloc(&d_rows, (size_t)n_steps * 8 * es));
   TFG_CUDA(cudaMalloc(&d_gmt, (size_t)n_steps * n_tz * es));
   if (x->mode == TFG_F32) {
-    std::string buf((size_t)n_steps * (6 + n_tz) * sizeof(float), '\0');
+    std::string buf((size_t)n_steps * (8 + n_tz) * sizeof(float), '\0');
     float* fr = reinterpret_cast<float*>(&buf[0]);
-    float* fg = fr + (size_t)n_steps * 6;
+    float* fg = fr + (size_t)n_steps * 8;
     const double* src = reinterpret_cast<const double*>(rows);
-    for (int64_t i = 0; i < n_steps * 6; ++i) fr[i] = (float)src[i];
+    for (int64_t i = 0; i < n_steps * 8; ++i) fr[i] = (float)src[i];
     for (int64_t i = 0; i < n_steps * n_tz; ++i) fg[i] = (float)gmt[i];
-    TFG_CUDA(cudaMemcpyAsync(d_rows, fr, (size_t)n_steps * 6 * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaMemcpyAsync(d_rows, fr, (size_t)n_steps * 8 * es, cudaMemcpyHostToDevice, s));
     TFG_CUDA(cudaMemcpyAsync(d_gmt, fg, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
     TFG_CUDA(cudaStreamSynchronize(s));
   } else {
-    TFG_CUDA(cudaMemcpyAsync(d_rows, rows, (size_t)n_steps * 6 * es, cudaMemcpyHostToDevice, s));
+    TFG_CUDA(cudaMemcpyAsync(d_rows, rows, (size_t)n_steps * 8 * es, cudaMemcpyHostToDevice, s));
     TFG_CUDA(cudaMemcpyAsync(d_gmt, gmt, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
     TFG_CUDA(cudaStreamSynchronize(s));
   }

@@ -1,0 +1,142 @@
+// tfg_math.cuh -- lean double-precision elementary functions for the FAST arithmetic mode.
+//
+// Why not libdevice: in the melt kernel ~70 % of all issued instructions were not FP64 math but the
+// 2 x UMOV immediates libdevice spends per polynomial coefficient, plus branches around special cases
+// (ncu, profiles/).  These versions keep coefficients in __constant__ memory (one LDCU.128 feeds two
+// DFMAs), are branch-free on their fast path, use a MUFU seed + two Newton steps for reciprocals, and are
+// accurate to <= ~2 ulp on the argument ranges the physics produces.  Anything outside the fast path
+// (non-finite, huge, non-positive log argument ...) falls back to libdevice, so semantics are preserved.
+//
+// The strict mode never uses this file: it stays on libdevice + single-rounding IEEE operations.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TFG_HD __host__ __device__ __forceinline__
+#else
+#define TFG_HD inline
+#define __constant__ static const
+#endif
+
+namespace tfg {
+namespace fm {
+
+#include "tfg_math_coeffs.inc"
+
+#if defined(__CUDA_ARCH__)
+#define TFG_COEF(tab, i) tab[i]
+__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
+__device__ __forceinline__ double mk64(int hi, int lo) { return __hiloint2double(hi, lo); }
+#else
+#define TFG_COEF(tab, i) tab[i]
+inline int hi32(double x) { long long b; __builtin_memcpy(&b, &x, 8); return (int)(b >> 32); }
+inline int lo32(double x) { long long b; __builtin_memcpy(&b, &x, 8); return (int)(b & 0xffffffffll); }
+inline double mk64(int hi, int lo) {
+  long long b = ((long long)hi << 32) | (unsigned int)lo; double x; __builtin_memcpy(&x, &b, 8); return x;
+}
+#endif
+
+template <int N>
+TFG_HD double horner(const double (&c)[N], double x) {
+  double p = c[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) p = fma(p, x, c[i]);
+  return p;
+}
+
+// 1/b for finite, normal, non-zero b: MUFU.RCP64H seed (~2^-23) + two Newton steps.
+TFG_HD double rcp(double b) {
+  double r;
+#if defined(__CUDA_ARCH__)
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#else
+  r = (double)(1.0f / (float)b);
+#endif
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+// a/b with one residual correction (<= ~0.6 ulp); b finite, normal, non-zero
+TFG_HD double div(double a, double b) {
+  const double r = rcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+// sqrt(w) for w >= 0 (w below 1e-290 is treated as 1e-290): MUFU.RSQ64H seed + Newton
+TFG_HD double sqrt_pos(double w) {
+  w = fmax(w, 1e-290);
+  double y;
+#if defined(__CUDA_ARCH__)
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+#else
+  y = (double)(1.0f / sqrtf((float)w));
+#endif
+  double h = 0.5 * w;
+  y = y * fma(-h * y, y, 1.5);   // two Newton steps on 1/sqrt
+  y = y * fma(-h * y, y, 1.5);
+  double s = w * y;
+  return fma(fma(-s, s, w), 0.5 * y, s);  // Heron correction
+}
+
+// exp(x), |x| < 700
+TFG_HD double exp_core(double x) {
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // low word = rint(x*log2(e))
+  const int n = lo32(t);
+  const double fn = t - 6755399441055744.0;
+  double r = fma(fn, -6.93147180369123816490e-01, x);
+  r = fma(fn, -1.90821492927058770002e-10, r);
+  const double q = horner(kExpQ, r);
+  const double p = fma(q, r * r, r) + 1.0;  // in [0.70, 1.42]
+  return mk64(hi32(p) + (n << 20), lo32(p));
+}
+TFG_HD double exp_f(double x) { return (fabs(x) < 700.0) ? exp_core(x) : exp(x); }
+
+// log(x) for positive, normal, finite x
+TFG_HD double log_core(double x) {
+  int hi = hi32(x);
+  int e = (hi >> 20) - 1023;
+  double m = mk64((hi & 0x000fffff) | 0x3ff00000, lo32(x));  // [1, 2)
+  const bool up = m > 1.4142135623730951;
+  m = up ? 0.5 * m : m;                                        // [0.707, 1.414]
+  e = up ? e + 1 : e;
+  const double f = m - 1.0;                                    // exact
+  const double s = div(f, 2.0 + f);
+  const double z = s * s;
+  const double lm = fma(s * z, horner(kLogP, z), 2.0 * s);     // log(m) = 2 atanh(s)
+  const double ed = (double)e;
+  return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lm));
+}
+TFG_HD double log_f(double x) {
+  const unsigned hi = (unsigned)hi32(x);
+  return (hi - 0x00100000u < 0x7fe00000u) ? log_core(x) : log(x);
+}
+
+// x**y for x > 0 (normal, finite): exp(y*log(x)); relative error ~ (|y*log x| + 2) ulp
+TFG_HD double pow_f(double x, double y) { return exp_f(y * log_f(x)); }
+
+// asin(x) for 0 <= x <= 1 (values slightly above 1 are clamped)
+TFG_HD double asin01(double x) {
+  const bool big = x > 0.5;
+  const double w = big ? fmax(0.5 * (1.0 - x), 0.0) : x * x;
+  const double s = big ? sqrt_pos(w) : x;
+  const double a = fma(s * w, horner(kAsinP, w), s);
+  // pi/2 = 1.5707963267948966 + 6.123233995736766e-17
+  return big ? (fma(-2.0, a, 1.5707963267948966) + 6.123233995736766e-17) : a;
+}
+
+// atan(x), any finite x
+TFG_HD double atan_f(double x) {
+  const double ax = fabs(x);
+  if (!(ax < 1e150)) return atan(x);
+  const bool inv = ax > 1.0;
+  const double t = inv ? rcp(ax) : ax;
+  const double a0 = t * horner(kAtanP, t * t);
+  const double a = inv ? ((1.5707963267948966 - a0) + 6.123233995736766e-17) : a0;
+  return copysign(a, x);
+}
+
+}  // namespace fm
+}  // namespace tfg

@@ -39,17 +39,24 @@ struct Consts {
   raw omega;         // 15 deg/h in rad (solar_funcs.py:257-258)
   raw rad2deg;       // 180 / pi (solar_funcs.py:550)
   raw deg2rad;       // pi / 180 (solar_funcs.py:566)
+  raw inv_z0, inv_dt, inv_rho_lf;  // fast modes only: reciprocals of z0_air, dt, rho_H2O*Lf
   int satterlund;
 };
 
 template <class raw>
 struct TimeRow {  // see tfg_time_row in include/tfglacier.h
   raw clock_hour, TE, sin_decl, cos_decl, tan_decl, isc_e0;
+  raw cos_hour, sin_hour;  // cos/sin of omega*((clock_hour - 12) - TE); fast modes only
 };
 
 template <class raw>
 struct CellStatic {
   raw a_elev, sin_lat, cos_lat, neg_tan_lat, sin_eq, cos_eq, neg_tan_eq, dlon, t_noon, da_m2, t_rs;
+};
+
+template <class raw>
+struct CellAngles {  // fast modes: cos/sin of B = omega*LC and of B - dlon (per cell, changes only with the UTC offset)
+  raw cB, sB, cB2, sB2;
 };
 
 template <class raw>
@@ -80,7 +87,7 @@ __device__ __forceinline__ Num<P> e_sat_mbar(const Consts<typename P::raw>& k, N
     e_sat = R(0.611) * nexp(term1);
   } else {
     R term1 = R(2353.0) / (T + 273.15);
-    e_sat = npow(R(10.0), R(11.4) - term1) / 1000.0;
+    e_sat = divk(npow(R(10.0), R(11.4) - term1), 1000.0);
   }
   return e_sat * 10.0;
 }
@@ -88,13 +95,23 @@ __device__ __forceinline__ Num<P> e_sat_mbar(const Consts<typename P::raw>& k, N
 // The clock- and cell-dependent part of Clear_Sky_Radiation; returns K_cs.
 template <class P>
 __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
-                                            const CellStatic<typename P::raw>& s, Num<P> th, Num<P> W_p,
+                                            const CellStatic<typename P::raw>& s,
+                                            const CellAngles<typename P::raw>& ang, Num<P> th, Num<P> W_p,
                                             Num<P> albedo) {
   using R = Num<P>;
   const R sin_d(tr.sin_decl), cos_d(tr.cos_decl), tan_d(tr.tan_decl), omega(k.omega);
   const R wt = omega * th;
-  const R c_wt = ncos(wt);                                   // cos(omega*th), solar_funcs.py:282, :391
-  const R c_u = ncos(wt + R(s.dlon));                        // solar_funcs.py:867
+  R c_wt, c_u;
+  if constexpr (P::strict) {
+    c_wt = ncos(wt);                                         // cos(omega*th), solar_funcs.py:282, :391
+    c_u = ncos(wt + R(s.dlon));                              // solar_funcs.py:867
+  } else {
+    // omega*th = A_t - B_c with A_t = omega*((clock-12)-TE) (host, per step) and B_c = omega*LC (per cell):
+    // cos(A - B) = cosA cosB + sinA sinB -- two FMAs instead of a full-range cos()
+    const R cA(tr.cos_hour), sA(tr.sin_hour);
+    c_wt = (cA * R(ang.cB)) + (sA * R(ang.sB));
+    c_u = (cA * R(ang.cB2)) + (sA * R(ang.sB2));
+  }
   // sunrise / sunset arguments, solar_funcs.py:325-326 (horizontal) and :796 (equivalent latitude)
   const R arg_eq = nmin(nmax(R(-1.0), R(s.neg_tan_eq) * tan_d), R(1.0));
   const R arg_h = nmin(nmax(R(-1.0), R(s.neg_tan_lat) * tan_d), R(1.0));
@@ -116,14 +133,20 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
 
   // Zenith_Angle solar_funcs.py:281-284
   const R cosZ = (R(s.sin_lat) * sin_d) + ((R(s.cos_lat) * cos_d) * c_wt);
-  const R Z = nacos(cosZ);
   // Optical_Air_Mass solar_funcs.py:549-568 (Kasten & Young 1989)
-  R gamma = R(90.0) - (Z * R(k.rad2deg));
-  gamma = sel(R(0.0) > gamma, R(0.0), gamma);
-  R t1;
-  if constexpr (P::strict) t1 = nsin(gamma * R(k.deg2rad));
-  else t1 = nmax(cosZ, R(0.0));                              // sin(90deg - Z) == cos Z
-  const R t2 = R(0.50572) / npow(gamma + 6.07995, R(1.6364));
+  R gamma, t1, t2;
+  if constexpr (P::strict) {
+    const R Z = nacos(cosZ);
+    gamma = R(90.0) - (Z * R(k.rad2deg));
+    gamma = sel(R(0.0) > gamma, R(0.0), gamma);
+    t1 = nsin(gamma * R(k.deg2rad));
+    t2 = R(0.50572) / npow(gamma + 6.07995, R(1.6364));
+  } else {
+    // elevation angle gamma = 90deg - Z = asin(cos Z), sin(gamma) = cos Z; a/(gamma+b)^c = a*exp(-c*log(gamma+b))
+    t1 = nmax(cosZ, R(0.0));
+    gamma = nasin01(t1) * R(k.rad2deg);
+    t2 = R(0.50572) * nexp(R(-1.6364) * nlog(gamma + 6.07995));
+  }
   const R M_opt = R(1.0) / (t1 + t2);
   // Atmospheric_Transmissivity solar_funcs.py:608-614
   const R a_sa = R(-0.1240) - (R(0.0207) * W_p);
@@ -148,7 +171,8 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
 template <class P, bool VOL, class WindowFn>
 __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
-                                          const CellStatic<typename P::raw>& s, Num<P> LC,
+                                          const CellStatic<typename P::raw>& s,
+                                          const CellAngles<typename P::raw>& ang, Num<P> LC,
                                           CellState<typename P::raw>& st, CellVol<typename P::raw>& vol,
                                           Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
                                           WindowFn&& window_sum, StepOut<typename P::raw>& o) {
@@ -159,7 +183,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
   const R T_K = T_air + 273.15;
   R p0 = R(k.sea_p0) * nexp(R(s.a_elev) / (R(k.r_star) * T_K));
-  p0 = (p0 / 1000.0) * 10.0;
+  if constexpr (P::strict) p0 = (p0 / 1000.0) * 10.0; else p0 = p0 * 0.01;
   // ---- update_P_rain :585, update_P_snow :604  (P * bool)
   const bool is_rain = T_air > R(s.t_rs);
   const bool is_snow = T_air <= R(s.t_rs);
@@ -181,10 +205,11 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- vapour pressures :423-425
   const R e_sat_air = e_sat_mbar<P>(k, T_air);
   R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));     // :817
-  const R e_air = (e / 1000.0) * 10.0;                       // :818-821
+  R e_air;                                                   // :818-821
+  if constexpr (P::strict) e_air = (e / 1000.0) * 10.0; else e_air = e * 0.01;
   const R RH = e_air / e_sat_air;                            // :838
   // ---- update_dew_point :888-893
-  const R log_term = nlog(e_air / 6.1121);
+  const R log_term = nlog(divk(e_air, 6.1121));
   const R T_dew = (R(257.14) * log_term) / (R(18.678) - log_term);
   // ---- update_T_surf :906-911
   const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
@@ -197,7 +222,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   bot = sel(bot == 0.0, R(0.01), bot);
   const R Ri = top / bot;
   // ---- update_bulk_aero_conductance :670-733
-  const R arg = R(k.kappa) / nlog(nmax((R(k.z) - h_snow) / R(k.z0_air), R(0.01)));
+  R zr;
+  if constexpr (P::strict) zr = (R(k.z) - h_snow) / R(k.z0_air); else zr = (R(k.z) - h_snow) * R(k.inv_z0);
+  const R arg = R(k.kappa) / nlog(nmax(zr, R(0.01)));
   const R Dn = uz * (arg * arg);
   R Dh;
   if (T_air == T_surf) Dh = Dn;
@@ -225,16 +252,16 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if (h_snow == 0.0 && h_ice > 0.0) albedo = R(0.3);         // :1049-1053
   if (h_snow == 0.0 && h_ice == 0.0) albedo = R(0.15);       // :1054-1058
   // ---- update_net_shortwave_radiation :1122-1139
-  const R K_cs = clear_sky<P>(k, tr, s, th, W_p, albedo);
+  const R K_cs = clear_sky<P>(k, tr, s, ang, th, W_p, albedo);
   const R Qn_SW = K_cs * (R(1.0) - albedo);
   // ---- update_em_air :1167-1192
   R em_air;
   if (!k.satterlund) {
-    const R x = (e_air / 10.0) / T_K;
+    const R x = divk(e_air, 10.0) / T_K;
     const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
     em_air = (term1 * R(k.emis_b)) + R(k.canopy);
   } else {
-    em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, T_K / 2016.0)));
+    em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, divk(T_K, 2016.0))));
   }
   // ---- update_net_longwave_radiation :1231-1248
   const R T_surf_K = T_surf + 273.15;
@@ -249,7 +276,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- snow: update_snow_meltrate :1364-1368, enforce_max_snow_meltrate :1465
   const R previous_swe = h_swe;                              // :1571
   const R E_in = Q_sum * dt;
-  R SM = (nmax(E_in - Eccs, R(0.0)) / dt) / R(k.rho_lf);
+  R SM;
+  if constexpr (P::strict) SM = (nmax(E_in - Eccs, R(0.0)) / dt) / R(k.rho_lf);
+  else SM = (nmax(E_in - Eccs, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf);
   SM = nmax(SM, R(0.0));
   if constexpr (VOL) vol.vol_SM = (R(vol.vol_SM) + (((SM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
@@ -269,19 +298,21 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     Eccs = nmax((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in, R(0.0));
   }
   // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
-  R IM = nmax((nmax(E_in - Ecci, R(0.0)) / dt) / R(k.rho_lf), R(0.0));
+  R IM;
+  if constexpr (P::strict) IM = nmax((nmax(E_in - Ecci, R(0.0)) / dt) / R(k.rho_lf), R(0.0));
+  else IM = nmax((nmax(E_in - Ecci, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf), R(0.0));
   IM = sel((h_swe == 0.0) && (previous_swe == 0.0), IM, R(0.0));
   Ecci = nmax(Ecci - E_in, R(0.0));
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
-  IM = nmax(nmin(IM, h_iwe / dt), R(0.0));
+  if constexpr (P::strict) IM = nmax(nmin(IM, h_iwe / dt), R(0.0)); else IM = nmax(nmin(IM, h_iwe * R(k.inv_dt)), R(0.0));
   if constexpr (VOL) vol.vol_IM = (R(vol.vol_IM) + (((IM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
   IM = xdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
   h_iwe = nmax(h_iwe, R(0.0));
   // ---- update_combined_meltrate :1441-1445
-  const R M_total = (IM + SM) + (P_rain / 3600.0);
+  const R M_total = (IM + SM) + divk(P_rain, 3600.0);
   // ---- update_snow_depth :1711, update_ice_depth :1726
   h_snow = xmul(h_swe, R(k.ws_ratio));
   h_ice = xmul(h_iwe, R(k.wi_ratio));

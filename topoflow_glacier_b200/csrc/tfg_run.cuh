@@ -12,7 +12,13 @@
 
 namespace tfg {
 
-constexpr int kBlock = 128;
+#ifndef TFG_BLOCK
+#define TFG_BLOCK 128
+#endif
+#ifndef TFG_MIN_BLOCKS
+#define TFG_MIN_BLOCKS 3
+#endif
+constexpr int kBlock = TFG_BLOCK;
 
 template <class raw>
 struct RunParams {
@@ -68,7 +74,7 @@ __device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int
 }
 
 template <class P, bool REC, bool AGG, bool VOL>
-__global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
+__global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
   using raw = typename P::raw;
   using R = Num<P>;
   const int64_t gid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -120,8 +126,18 @@ __global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ Run
       f4 = ld_stream(f + 4 * N);
   raw r_old = ring[(int64_t)slot * N];
   R LC(0.0);
-  raw gmt_prev = p.gmt[p.step0 * p.n_tz + tz];
-  LC = ((R(gmt_prev) * 15.0) - lon) / 15.0;  // True_Solar_Noon, solar_funcs.py:1466-1468
+  CellAngles<raw> ang = {0, 0, 0, 0};
+  auto set_zone = [&](raw gmt) {
+    if constexpr (P::strict) {
+      LC = ((R(gmt) * 15.0) - lon) / 15.0;  // True_Solar_Noon, solar_funcs.py:1466-1468
+    } else {
+      LC = ((R(gmt) * 15.0) - lon) * R(1.0 / 15.0);
+      const raw B = p.k.omega * LC.v;
+      if constexpr (P::f32) { __sincosf(B, &ang.sB, &ang.cB); __sincosf(B - s.dlon, &ang.sB2, &ang.cB2); }
+      else { sincos(B, &ang.sB, &ang.cB); sincos(B - s.dlon, &ang.sB2, &ang.cB2); }
+    }
+  };
+  raw gmt_prev = __longlong_as_double(0x7ff8000000000000ll);  // NaN: the first step always sets the zone
 
   StepOut<raw> o;
   for (int t = 0; t < p.n_steps; ++t) {
@@ -134,9 +150,9 @@ __global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ Run
     const int64_t step = p.step0 + t;
     const TimeRow<raw> row = p.rows[step];
     const raw gmt = p.gmt[step * p.n_tz + tz];
-    if (gmt != gmt_prev) {  // DST switch: piece-wise constant in time
+    if (!(gmt == gmt_prev)) {  // first step, or DST switch (the offset is piece-wise constant in time)
       gmt_prev = gmt;
-      LC = ((R(gmt) * 15.0) - lon) / 15.0;
+      set_zone(gmt);
     }
     const int slot_next = (slot + 1 == slots) ? 0 : slot + 1;
     raw r_next = 0;
@@ -157,7 +173,7 @@ __global__ void __launch_bounds__(kBlock) run_kernel(const __grid_constant__ Run
       r_next = ring[(int64_t)slot_next * N];  // next step's oldest entry (after this step's store)
       return tot_now;
     };
-    cell_step<P, VOL>(p.k, row, s, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+    cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
 
     if constexpr (REC) {
       if (active && p.record != nullptr) {

@@ -164,7 +164,8 @@ class MeltEngine:
         n = max(n_steps, 2 * self._n_time)
         tt = time_tables(self.start, self.dt_hours, n)
         rows = np.ascontiguousarray(np.stack([tt[k] for k in ("clock_hour", "TE", "sin_decl", "cos_decl", "tan_decl",
-                                                                "isc_e0")], axis=1), dtype=np.float64)
+                                                                "isc_e0", "cos_hour", "sin_hour")], axis=1),
+                                    dtype=np.float64)
         gmt = utc_offsets(tt["when"], self.zones)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.tfg_bind_time(self.ctx, rows.ctypes.data, gmt.ctypes.data, n, gmt.shape[1], stream),

@@ -82,7 +82,10 @@ def time_tables(start: pd.Timestamp, dt_hours, n_steps: int) -> dict[str, np.nda
              - (np.float64(0.002697) * np.cos(np.float64(3) * G)) + (np.float64(0.001480) * np.sin(np.float64(3) * G)))
     E0 = (np.float64(1.000110) + (np.float64(0.034221) * np.cos(G)) + (np.float64(0.001280) * np.sin(G))
           + (np.float64(0.000719) * np.cos(np.float64(2) * G)) + (np.float64(0.000077) * np.sin(np.float64(2) * G)))
+    omega = (np.float64(360) / np.float64(24)) * (np.pi / np.float64(180))
+    hour_angle = omega * ((clock_hour - np.float64(12)) - TE)  # omega*th + omega*LC (fast modes)
     return {
+        "cos_hour": np.cos(hour_angle), "sin_hour": np.sin(hour_angle),
         "when": when, "julian_day": jd, "clock_hour": clock_hour, "TE": TE, "delta": delta, "E0": E0,
         "sin_decl": np.sin(delta), "cos_decl": np.cos(delta), "tan_decl": np.tan(delta),
         "isc_e0": np.float64(1361.5) * E0,
