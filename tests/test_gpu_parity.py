@@ -180,8 +180,14 @@ def test_large_random_sample_with_knife_edges(mode, cuda_device):
     got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).to(cuda_device), record=keys).items()}
     eng.close()
     mask = knife_edge_mask(got, want)
+    # the log-law drag coefficient kappa/log((z - h_snow)/z0) (reference :670) is singular at h_snow = z - z0 =
+    # 9.99 m: within a few cm of it a 1-ulp change of h_snow moves Qh/Qe by >1e-12 relative in ANY implementation
+    hs = np.vstack([statics["h0_snow"][None, :], want["h_snow"]])
+    singular = ((hs > 9.9) & (hs < 10.0)).any(axis=0)
+    mask |= singular[None, :]
     melted = int(((want["h_swe"][0] > 0) & (want["h_swe"][-1] == 0)).sum())
-    rep = {"cells": N, "steps": T, "cells_melted_out": melted, "knife_edge_cells": int(mask[-1].sum())}
+    rep = {"cells": N, "steps": T, "cells_melted_out": melted, "knife_edge_cells": int(mask[-1].sum() - singular.sum()),
+           "log_law_singular_cells": int(singular.sum())}
     bad = []
     for k in keys:
         ok, ratio, dabs, drel = err_report(got[k][~mask], want[k][~mask], ATOL[k])
@@ -190,5 +196,5 @@ def test_large_random_sample_with_knife_edges(mode, cuda_device):
             bad.append((k, ratio, dabs, drel))
     _dump(f"random16k/{mode}", rep)
     assert melted > 100
-    assert mask[-1].sum() <= max(5, 0.15 * melted), rep
+    assert rep["knife_edge_cells"] <= max(5, 0.15 * melted) and singular.sum() <= 0.05 * N, rep
     assert not bad, bad
