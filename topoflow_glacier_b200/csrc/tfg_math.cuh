@@ -127,16 +127,16 @@ TFG_HD double asin01(double x) {
   return big ? (fma(-2.0, a, 1.5707963267948966) + 6.123233995736766e-17) : a;
 }
 
-// atan(x), any finite x
-TFG_HD double atan_f(double x) {
+// atan(x), |x| < 1e150
+TFG_HD double atan_core(double x) {
   const double ax = fabs(x);
-  if (!(ax < 1e150)) return atan(x);
   const bool inv = ax > 1.0;
   const double t = inv ? rcp(ax) : ax;
   const double a0 = t * horner(kAtanP, t * t);
   const double a = inv ? ((1.5707963267948966 - a0) + 6.123233995736766e-17) : a0;
   return copysign(a, x);
 }
+TFG_HD double atan_f(double x) { return (fabs(x) < 1e150) ? atan_core(x) : atan(x); }
 
 }  // namespace fm
 }  // namespace tfg

@@ -17,9 +17,12 @@
 
 namespace tfg {
 
-struct StrictF64 { using raw = double; static constexpr bool strict = true;  static constexpr bool f32 = false; };
-struct FastF64   { using raw = double; static constexpr bool strict = false; static constexpr bool f32 = false; };
-struct FastF32   { using raw = float;  static constexpr bool strict = false; static constexpr bool f32 = true;  };
+// `lean`: use the guard-free cores of tfg_math.cuh (valid only for physically sane arguments; the kernel
+// checks the forcings of a warp each step and otherwise runs the same step under SafeF64).
+struct StrictF64 { using raw = double; static constexpr bool strict = true,  f32 = false, lean = false; };
+struct FastF64   { using raw = double; static constexpr bool strict = false, f32 = false, lean = true;  };
+struct SafeF64   { using raw = double; static constexpr bool strict = false, f32 = false, lean = false; };
+struct FastF32   { using raw = float;  static constexpr bool strict = false, f32 = true,  lean = false; };
 
 template <class P>
 struct Num {
@@ -44,7 +47,8 @@ template <class P> __device__ __forceinline__ Num<P> operator*(Num<P> a, Num<P> 
 template <class P> __device__ __forceinline__ Num<P> operator/(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>(__ddiv_rn(a.v, b.v));
   else if constexpr (P::f32) return Num<P>(__fdividef(a.v, b.v));
-  else return Num<P>(fm::div(a.v, b.v));
+  else if constexpr (P::lean) return Num<P>(fm::div(a.v, b.v));
+  else return Num<P>(a.v / b.v);
 }
 // division by a compile-time constant: a true division in strict mode, a multiplication by the
 // (compile-time) reciprocal otherwise
@@ -105,17 +109,18 @@ template <class P> __device__ __forceinline__ Num<P> xdiv(Num<P> a, Num<P> b) {
 template <class P> __device__ __forceinline__ Num<P> nsqrt(Num<P> a) {
   if constexpr (P::strict) return Num<P>(__dsqrt_rn(a.v));
   else if constexpr (P::f32) return Num<P>(__fsqrt_rn(a.v));
-  else return Num<P>(fm::sqrt_pos(a.v));
+  else if constexpr (P::lean) return Num<P>(fm::sqrt_pos(a.v));
+  else return Num<P>(sqrt(a.v));
 }
 template <class P> __device__ __forceinline__ Num<P> nexp(Num<P> a) {
   if constexpr (P::f32) return Num<P>(__expf(a.v));
-  else if constexpr (P::strict) return Num<P>(exp(a.v));
-  else return Num<P>(fm::exp_f(a.v));
+  else if constexpr (P::lean) return Num<P>(fm::exp_core(a.v));
+  else return Num<P>(exp(a.v));
 }
 template <class P> __device__ __forceinline__ Num<P> nlog(Num<P> a) {
   if constexpr (P::f32) return Num<P>(__logf(a.v));
-  else if constexpr (P::strict) return Num<P>(log(a.v));
-  else return Num<P>(fm::log_f(a.v));
+  else if constexpr (P::lean) return Num<P>(fm::log_core(a.v));
+  else return Num<P>(log(a.v));
 }
 template <class P> __device__ __forceinline__ Num<P> nsin(Num<P> a) {
   if constexpr (P::f32) return Num<P>(__sinf(a.v)); else return Num<P>(sin(a.v));
@@ -125,22 +130,25 @@ template <class P> __device__ __forceinline__ Num<P> ncos(Num<P> a) {
 }
 template <class P> __device__ __forceinline__ Num<P> natan(Num<P> a) {
   if constexpr (P::f32) return Num<P>(atanf(a.v));
-  else if constexpr (P::strict) return Num<P>(atan(a.v));
-  else return Num<P>(fm::atan_f(a.v));
+  else if constexpr (P::lean) return Num<P>(fm::atan_core(a.v));
+  else return Num<P>(atan(a.v));
 }
 template <class P> __device__ __forceinline__ Num<P> nacos(Num<P> a) {
   if constexpr (P::f32) return Num<P>(acosf(a.v)); else return Num<P>(acos(a.v));
 }
 // asin(x)*(180/pi) for x in [0,1] (fast modes only): the solar elevation angle in degrees
 template <class P> __device__ __forceinline__ Num<P> nasin01(Num<P> a) {
-  if constexpr (P::f32) return Num<P>(asinf(fminf(a.v, 1.0f))); else return Num<P>(fm::asin01(a.v));
+  if constexpr (P::f32) return Num<P>(asinf(fminf(a.v, 1.0f)));
+  else if constexpr (P::lean) return Num<P>(fm::asin01(a.v));
+  else return Num<P>(asin(fmin(a.v, 1.0)));
 }
 // x**y for x > 0.  Strict: libdevice pow (NumPy calls its own / libm's pow).  Fast: exp(y*log(x)),
 // whose relative error is ~|y*log(x)| ulp -- far inside the 1e-12 budget for the exponents used here.
 template <class P> __device__ __forceinline__ Num<P> npow(Num<P> x, Num<P> y) {
   if constexpr (P::strict) return Num<P>(pow(x.v, y.v));
   else if constexpr (P::f32) return Num<P>(__expf(y.v * __logf(x.v)));
-  else return Num<P>(fm::pow_f(x.v, y.v));
+  else if constexpr (P::lean) return Num<P>(fm::exp_core(y.v * fm::log_core(x.v)));
+  else return Num<P>(exp(y.v * log(x.v)));
 }
 template <class P> __device__ __forceinline__ Num<P> npow4(Num<P> x) {  // x**4.0
   if constexpr (P::strict) return Num<P>(pow(x.v, 4.0));

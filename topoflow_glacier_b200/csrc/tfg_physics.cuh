@@ -243,7 +243,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_albedo("aging") :1023-1059
   const R r = sel(T_air > 0.0, R(0.12), R(0.05));
   const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
-  const R tot = window_sum(ring_new);                        // :1027-1037
+  const R tot(window_sum(ring_new.v));                       // :1027-1037
   R n(st.n_days);
   n = sel(tot >= 0.03, R(0.0), n);                           // :1040
   n = sel(tot < 0.03, n + R(k.days_per_dt), n);              // :1041

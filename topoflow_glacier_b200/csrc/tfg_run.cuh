@@ -139,6 +139,13 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
   };
   raw gmt_prev = __longlong_as_double(0x7ff8000000000000ll);  // NaN: the first step always sets the zone
 
+  bool statics_sane = true;
+  if constexpr (P::lean) {  // finite tables with |a_elev| < 1e3 (|elev| < 3.5 km ... 1e6 m is still fine for exp)
+    auto finite = [](raw v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) != 0x7ff00000u; };
+    statics_sane = finite(s.a_elev) && fabs(s.a_elev) < 2.0e5 && finite(s.sin_lat) && finite(s.cos_lat) &&
+                   finite(s.neg_tan_lat) && finite(s.sin_eq) && finite(s.cos_eq) && finite(s.neg_tan_eq) &&
+                   finite(s.dlon) && finite(s.t_noon) && finite(s.t_rs) && finite(lon.v);
+  }
   StepOut<raw> o;
   for (int t = 0; t < p.n_steps; ++t) {
     raw g0 = f0, g1 = f1, g2 = f2, g3 = f3, g4 = f4;
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
     const int slot_next = (slot + 1 == slots) ? 0 : slot + 1;
     raw r_next = 0;
     R tot_now;
-    auto window = [&](R ring_new) -> R {
+    auto window = [&](raw ring_new_raw) -> raw {
+      const R ring_new(ring_new_raw);
       if (active) ring[(int64_t)slot * N] = ring_new.v;  // np.roll(-1) + write of the newest slot, :1027-1033
       if (exact) {
         tot_now = window_sum_exact<P>(ring, N, slots, slot);
@@ -171,9 +179,28 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
         tot_now = tot;
       }
       r_next = ring[(int64_t)slot_next * N];  // next step's oldest entry (after this step's store)
-      return tot_now;
+      return tot_now.v;
     };
-    cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+    if constexpr (P::lean) {
+      // The lean math cores assume physically sane arguments.  Bit tests on the high words (no FP64 pipe):
+      // P in [0, 10) m/h, |T_air| < 90 degC, P_air in [1e3, 2e5) Pa, q in [1e-7, 0.2), uz = 0 or in [1e-100, 200)
+      auto in_range = [](raw v, double lo, double hi) {
+        const unsigned h = (unsigned)__double2hiint(v), l = (unsigned)__double2hiint(lo), u = (unsigned)__double2hiint(hi);
+        return (h - l) < (u - l);
+      };
+      const bool sane = ((unsigned)__double2hiint(f0) < (unsigned)__double2hiint(10.0)) &&
+                        (((unsigned)__double2hiint(f1) & 0x7fffffffu) < (unsigned)__double2hiint(90.0)) &&
+                        in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
+                        (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
+      if (__all_sync(0xffffffffu, sane)) {
+        cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+      } else {  // same step with libdevice functions and IEEE division: any input, reference semantics
+        using S = Num<SafeF64>;
+        cell_step<SafeF64, VOL>(p.k, row, s, ang, S(LC.v), st, vol, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
+      }
+    } else {
+      cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+    }
 
     if constexpr (REC) {
       if (active && p.record != nullptr) {
