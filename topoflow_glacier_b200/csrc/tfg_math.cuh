@@ -45,6 +45,27 @@ TFG_HD double horner(const double (&c)[N], double x) {
   return p;
 }
 
+// The same polynomial evaluated as K interleaved Horner chains in x^K (K = 2 or 4): K independent dependency
+// chains of length ~N/K instead of one of length N.  The melt kernel runs ~3 warps per scheduler and is bound by
+// DFMA latency, not throughput (ncu: "wait" is the dominant stall), so instruction-level parallelism pays.
+template <int K, int N>
+TFG_HD double horner_k(const double (&c)[N], double x) {
+  static_assert(K == 2 || K == 4, "K");
+  const double x2 = x * x;
+  const double y = (K == 2) ? x2 : x2 * x2;
+  double S[K];
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int jtop = ((N - 1 - r) / K) * K + r;  // highest power congruent to r (mod K); coefficient of x^j is c[N-1-j]
+    double acc = c[N - 1 - jtop];
+#pragma unroll
+    for (int j = jtop - K; j >= 0; j -= K) acc = fma(acc, y, c[N - 1 - j]);
+    S[r] = acc;
+  }
+  if (K == 2) return fma(x, S[1], S[0]);
+  return fma(x2, fma(x, S[3], S[2]), fma(x, S[1], S[0]));
+}
+
 // 1/b for finite, normal, non-zero b: MUFU.RCP64H seed (~2^-23) + two Newton steps.
 TFG_HD double rcp(double b) {
   double r;
@@ -88,7 +109,7 @@ TFG_HD double exp_core(double x) {
   const double fn = t - 6755399441055744.0;
   double r = fma(fn, -6.93147180369123816490e-01, x);
   r = fma(fn, -1.90821492927058770002e-10, r);
-  const double q = horner(kExpQ, r);
+  const double q = horner_k<2>(kExpQ, r);
   const double p = fma(q, r * r, r) + 1.0;  // in [0.70, 1.42]
   return mk64(hi32(p) + (n << 20), lo32(p));
 }
@@ -105,7 +126,7 @@ TFG_HD double log_core(double x) {
   const double f = m - 1.0;                                    // exact
   const double s = div(f, 2.0 + f);
   const double z = s * s;
-  const double lm = fma(s * z, horner(kLogP, z), 2.0 * s);     // log(m) = 2 atanh(s)
+  const double lm = fma(s * z, horner_k<2>(kLogP, z), 2.0 * s);     // log(m) = 2 atanh(s)
   const double ed = (double)e;
   return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lm));
 }
@@ -122,7 +143,7 @@ TFG_HD double asin01(double x) {
   const bool big = x > 0.5;
   const double w = big ? fmax(0.5 * (1.0 - x), 0.0) : x * x;
   const double s = big ? sqrt_pos(w) : x;
-  const double a = fma(s * w, horner(kAsinP, w), s);
+  const double a = fma(s * w, horner_k<2>(kAsinP, w), s);
   // pi/2 = 1.5707963267948966 + 6.123233995736766e-17
   return big ? (fma(-2.0, a, 1.5707963267948966) + 6.123233995736766e-17) : a;
 }
@@ -132,7 +153,7 @@ TFG_HD double atan_core(double x) {
   const double ax = fabs(x);
   const bool inv = ax > 1.0;
   const double t = inv ? rcp(ax) : ax;
-  const double a0 = t * horner(kAtanP, t * t);
+  const double a0 = t * horner_k<4>(kAtanP, t * t);
   const double a = inv ? ((1.5707963267948966 - a0) + 6.123233995736766e-17) : a0;
   return copysign(a, x);
 }

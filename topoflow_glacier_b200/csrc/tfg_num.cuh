@@ -50,10 +50,11 @@ template <class P> __device__ __forceinline__ Num<P> operator/(Num<P> a, Num<P> 
   else if constexpr (P::lean) return Num<P>(fm::div(a.v, b.v));
   else return Num<P>(a.v / b.v);
 }
+template <class P> __device__ __forceinline__ Num<P> zdiv(Num<P> a, Num<P> b);
 // division by a compile-time constant: a true division in strict mode, a multiplication by the
 // (compile-time) reciprocal otherwise
 template <class P> __device__ __forceinline__ Num<P> divk(Num<P> a, double c) {
-  if constexpr (P::strict) return Num<P>(__ddiv_rn(a.v, c));
+  if constexpr (P::strict) return zdiv(a, Num<P>(c));
   else return Num<P>(a.v * static_cast<typename P::raw>(1.0 / c));
 }
 template <class P> __device__ __forceinline__ Num<P> operator-(Num<P> a) { return Num<P>(-a.v); }
@@ -78,12 +79,12 @@ template <class P> __device__ __forceinline__ Num<P> sel(bool c, Num<P> a, Num<P
 template <class P> __device__ __forceinline__ Num<P> nmax(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>((a.v >= b.v) ? a.v : ((b.v > a.v) ? b.v : a.v + b.v));
   else if constexpr (P::f32) return Num<P>(fmaxf(a.v, b.v));
-  else return Num<P>(fmax(a.v, b.v));
+  else return Num<P>((a.v > b.v) ? a.v : b.v);  // 3 instructions; fmax() costs 6 (NaN canonicalisation)
 }
 template <class P> __device__ __forceinline__ Num<P> nmin(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>((a.v <= b.v) ? a.v : ((b.v < a.v) ? b.v : a.v + b.v));
   else if constexpr (P::f32) return Num<P>(fminf(a.v, b.v));
-  else return Num<P>(fmin(a.v, b.v));
+  else return Num<P>((a.v < b.v) ? a.v : b.v);
 }
 template <class P> __device__ __forceinline__ Num<P> nabs(Num<P> a) {
   if constexpr (P::f32) return Num<P>(fabsf(a.v)); else return Num<P>(fabs(a.v));
@@ -103,6 +104,16 @@ template <class P> __device__ __forceinline__ Num<P> xmul(Num<P> a, Num<P> b) {
 }
 template <class P> __device__ __forceinline__ Num<P> xdiv(Num<P> a, Num<P> b) {
   if constexpr (P::f32) return Num<P>(__fdiv_rn(a.v, b.v)); else return Num<P>(__ddiv_rn(a.v, b.v));
+}
+
+// a/b with a single rounding and full IEEE semantics, arranged so that a ZERO NUMERATOR never enters CUDA's
+// IEEE division: that routine sends a zero numerator down its ~100-instruction slow path, and if one lane of a
+// warp does, the whole warp waits -- melt rates and rain are zero most of the time.  For a == 0 the quotient is
+// a * (1/b): +-0 with the right sign, NaN for b = 0 or NaN.
+template <class P> __device__ __forceinline__ Num<P> zdiv(Num<P> a, Num<P> b) {
+  const bool z = (a.v == 0);
+  const Num<P> q = xdiv(Num<P>(z ? static_cast<typename P::raw>(1.0) : a.v), b);
+  return z ? xmul(a, q) : q;
 }
 
 // ---- transcendental functions ----------------------------------------------------------------------

@@ -10,6 +10,14 @@
 
 namespace tfg {
 
+// Numeric literals of the physics, kept in __constant__ memory: as immediates every float64 literal costs two
+// UMOV instructions per use; from the constant bank it is one LDCU (often hoisted out of the time loop).
+struct LitTable {
+  double mag_a, mag_b, esat0, c90, ky_a, ky_b, ky_c, ky_nc, sa_a0, sa_a1, sa_b0, sa_b1, s_a0, s_a1, s_b0, s_b1, dew_c, dew_b, wp_a, wp_b, alb_r1, alb_r0, alb_0, alb_k, alb_ice, alb_bare, st_a, st_b, st_c, st_d, st_e, st_f, kelvin, c12, snow_thr, c3600;
+};
+static __constant__ LitTable kLit = {17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0};
+#define LIT(field, value) (P::f32 ? Num<P>(value) : Num<P>(static_cast<typename P::raw>(kLit.field)))
+
 // host-precomputed scalars (products/ratios formed in the reference's own order)
 template <class raw>
 struct Consts {
@@ -83,8 +91,8 @@ __device__ __forceinline__ Num<P> e_sat_mbar(const Consts<typename P::raw>& k, N
   using R = Num<P>;
   R e_sat;
   if (!k.satterlund) {
-    R term1 = (R(17.3) * T) / (T + 237.3);
-    e_sat = R(0.611) * nexp(term1);
+    R term1 = (LIT(mag_a, 17.3) * T) / (T + LIT(mag_b, 237.3));
+    e_sat = LIT(esat0, 0.611) * nexp(term1);
   } else {
     R term1 = R(2353.0) / (T + 273.15);
     e_sat = divk(npow(R(10.0), R(11.4) - term1), 1000.0);
@@ -137,24 +145,24 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   R gamma, t1, t2;
   if constexpr (P::strict) {
     const R Z = nacos(cosZ);
-    gamma = R(90.0) - (Z * R(k.rad2deg));
+    gamma = LIT(c90, 90.0) - (Z * R(k.rad2deg));
     gamma = sel(R(0.0) > gamma, R(0.0), gamma);
     t1 = nsin(gamma * R(k.deg2rad));
-    t2 = R(0.50572) / npow(gamma + 6.07995, R(1.6364));
+    t2 = LIT(ky_a, 0.50572) / npow(gamma + LIT(ky_b, 6.07995), LIT(ky_c, 1.6364));
   } else {
     // elevation angle gamma = 90deg - Z = asin(cos Z), sin(gamma) = cos Z; a/(gamma+b)^c = a*exp(-c*log(gamma+b))
     t1 = nmax(cosZ, R(0.0));
     gamma = nasin01(t1) * R(k.rad2deg);
-    t2 = R(0.50572) * nexp(R(-1.6364) * nlog(gamma + 6.07995));
+    t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(gamma + LIT(ky_b, 6.07995)));
   }
   const R M_opt = R(1.0) / (t1 + t2);
   // Atmospheric_Transmissivity solar_funcs.py:608-614
-  const R a_sa = R(-0.1240) - (R(0.0207) * W_p);
-  const R b_sa = R(-0.0682) - (R(0.0248) * W_p);
+  const R a_sa = LIT(sa_a0, -0.1240) - (LIT(sa_a1, 0.0207) * W_p);
+  const R b_sa = LIT(sa_b0, -0.0682) - (LIT(sa_b1, 0.0248) * W_p);
   const R tau = nmin(nmax(nexp(a_sa + (b_sa * M_opt)) - R(k.dust), R(0.0)), R(1.0));
   // Scattering_Attenuation solar_funcs.py:649-653
-  const R a_s = R(-0.0363) - (R(0.0084) * W_p);
-  const R b_s = R(-0.0572) - (R(0.0173) * W_p);
+  const R a_s = LIT(s_a0, -0.0363) - (LIT(s_a1, 0.0084) * W_p);
+  const R b_s = LIT(s_b0, -0.0572) - (LIT(s_b1, 0.0173) * W_p);
   const R gam_s = (R(1.0) - nexp(a_s + (b_s * M_opt))) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
@@ -181,7 +189,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   R h_snow(st.h_snow), h_swe(st.h_swe), h_ice(st.h_ice), h_iwe(st.h_iwe), Eccs(st.eccs), Ecci(st.ecci);
 
   // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
-  const R T_K = T_air + 273.15;
+  const R T_K = T_air + LIT(kelvin, 273.15);
   R p0 = R(k.sea_p0) * nexp(R(s.a_elev) / (R(k.r_star) * T_K));
   if constexpr (P::strict) p0 = (p0 / 1000.0) * 10.0; else p0 = p0 * 0.01;
   // ---- update_P_rain :585, update_P_snow :604  (P * bool)
@@ -210,7 +218,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R RH = e_air / e_sat_air;                            // :838
   // ---- update_dew_point :888-893
   const R log_term = nlog(divk(e_air, 6.1121));
-  const R T_dew = (R(257.14) * log_term) / (R(18.678) - log_term);
+  const R T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
   // ---- update_T_surf :906-911
   const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
   const R T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);
@@ -233,24 +241,25 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_sensible_heat_flux :744-745
   const R Qh = (R(k.rho_cp_air) * Dh) * dT;
   // ---- update_precipitable_water_content :919-920
-  const R W_p = R(1.12) * nexp(R(0.0614) * T_dew);
+  const R W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);
   // ---- update_vapor_pressure(SURFACE=True) :853 ; update_latent_heat_flux :931-934
   const R e_surf = RH * e_sat_surf;
   const R Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
   // ---- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471
-  const R solar_noon = (R(12.0) + LC) + R(tr.TE);
+  const R solar_noon = (LIT(c12, 12.0) + LC) + R(tr.TE);
   const R th = R(tr.clock_hour) - solar_noon;
   // ---- update_albedo("aging") :1023-1059
-  const R r = sel(T_air > 0.0, R(0.12), R(0.05));
+  const R r = sel(T_air > 0.0, LIT(alb_r1, 0.12), LIT(alb_r0, 0.05));
   const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
   const R tot(window_sum(ring_new.v));                       // :1027-1037
   R n(st.n_days);
-  n = sel(tot >= 0.03, R(0.0), n);                           // :1040
-  n = sel(tot < 0.03, n + R(k.days_per_dt), n);              // :1041
+  const R thr = LIT(snow_thr, 0.03);
+  n = sel(tot >= thr, R(0.0), n);                           // :1040
+  n = sel(tot < thr, n + R(k.days_per_dt), n);              // :1041
   R albedo(st.albedo);
-  if (h_snow > 0.0) albedo = R(0.4) + (R(0.44) * nexp((-n) * r));  // :1042-1048
-  if (h_snow == 0.0 && h_ice > 0.0) albedo = R(0.3);         // :1049-1053
-  if (h_snow == 0.0 && h_ice == 0.0) albedo = R(0.15);       // :1054-1058
+  if (h_snow > 0.0) albedo = LIT(alb_0, 0.4) + (LIT(alb_k, 0.44) * nexp((-n) * r));  // :1042-1048
+  if (h_snow == 0.0 && h_ice > 0.0) albedo = LIT(alb_ice, 0.3);         // :1049-1053
+  if (h_snow == 0.0 && h_ice == 0.0) albedo = LIT(alb_bare, 0.15);       // :1054-1058
   // ---- update_net_shortwave_radiation :1122-1139
   const R K_cs = clear_sky<P>(k, tr, s, ang, th, W_p, albedo);
   const R Qn_SW = K_cs * (R(1.0) - albedo);
@@ -264,7 +273,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, divk(T_K, 2016.0))));
   }
   // ---- update_net_longwave_radiation :1231-1248
-  const R T_surf_K = T_surf + 273.15;
+  const R T_surf_K = T_surf + LIT(kelvin, 273.15);
   const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);
   R LW_out = R(k.es_sigma) * npow4(T_surf_K);
   LW_out = LW_out + (R(k.one_m_es) * LW_in);
@@ -277,38 +286,38 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R previous_swe = h_swe;                              // :1571
   const R E_in = Q_sum * dt;
   R SM;
-  if constexpr (P::strict) SM = (nmax(E_in - Eccs, R(0.0)) / dt) / R(k.rho_lf);
+  if constexpr (P::strict) SM = zdiv(zdiv(nmax(E_in - Eccs, R(0.0)), dt), R(k.rho_lf));
   else SM = (nmax(E_in - Eccs, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf);
   SM = nmax(SM, R(0.0));
   if constexpr (VOL) vol.vol_SM = (R(vol.vol_SM) + (((SM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
-  const R k3600(3600.0);
+  const R k3600 = LIT(c3600, 3600.0);
   h_swe = xadd(h_swe, xmul(P_snow, dt));
-  SM = xdiv(nmin(xmul(SM, k3600), h_swe), k3600);
+  SM = zdiv(nmin(xmul(SM, k3600), h_swe), k3600);
   h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
   h_swe = nmax(h_swe, R(0.0));
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
   if (P_snow > 0.0) {
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
-    const R T_wb = ((((T_air * natan(R(0.151977) * nsqrt(RH + 8.313659))) + natan(T_air + RH)) -
-                     natan(RH - 1.676331)) +
-                    ((R(0.00391838) * npow15(RH)) * natan(R(0.023101) * RH))) -
-                   4.86035;
+    const R T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
+                     natan(RH - LIT(st_c, 1.676331))) +
+                    ((LIT(st_d, 0.00391838) * npow15(RH)) * natan(LIT(st_e, 0.023101) * RH))) -
+                   LIT(st_f, 4.86035);
     const R del_T = R(k.T0) - T_wb;
     Eccs = nmax((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in, R(0.0));
   }
   // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
   R IM;
-  if constexpr (P::strict) IM = nmax((nmax(E_in - Ecci, R(0.0)) / dt) / R(k.rho_lf), R(0.0));
+  if constexpr (P::strict) IM = nmax(zdiv(zdiv(nmax(E_in - Ecci, R(0.0)), dt), R(k.rho_lf)), R(0.0));
   else IM = nmax((nmax(E_in - Ecci, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf), R(0.0));
   IM = sel((h_swe == 0.0) && (previous_swe == 0.0), IM, R(0.0));
   Ecci = nmax(Ecci - E_in, R(0.0));
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
-  if constexpr (P::strict) IM = nmax(nmin(IM, h_iwe / dt), R(0.0)); else IM = nmax(nmin(IM, h_iwe * R(k.inv_dt)), R(0.0));
+  if constexpr (P::strict) IM = nmax(nmin(IM, zdiv(h_iwe, dt)), R(0.0)); else IM = nmax(nmin(IM, h_iwe * R(k.inv_dt)), R(0.0));
   if constexpr (VOL) vol.vol_IM = (R(vol.vol_IM) + (((IM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
-  IM = xdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
+  IM = zdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
   h_iwe = nmax(h_iwe, R(0.0));
   // ---- update_combined_meltrate :1441-1445
