@@ -1,0 +1,55 @@
+"""Condense gpurun_out/ artefacts into the tracked profiles/ directory (round-tagged)."""
+import collections, csv, io, json, subprocess, sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT, SRC = ROOT / "profiles", ROOT / "gpurun_out"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+OUT.mkdir(exist_ok=True)
+
+
+def launches(csv_path: Path, dst: Path):
+    rows = [r for r in csv.reader(open(csv_path)) if len(r) > 14 and r[0].isdigit()]
+    agg = collections.OrderedDict()
+    for r in rows:
+        name = r[4].split("(")[0][:110]
+        if "run_kernel" in r[4]:
+            name = r[4].split("(RunParams")[0]
+        d = agg.setdefault(name, [0, 0.0])
+        d[0] += 1
+        d[1] += float(r[14].replace(",", "")) / (1e3 if r[13] == "us" else 1e6 if r[13] == "ns" else 1.0)  # -> ms
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list ({csv_path.name}); durations are cold-cache, serialised: compare SHARES\n")
+        f.write("kernel,launches,total_ms,share\n")
+        for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"\"{k}\",{n},{ms:.3f},{ms / tot:.4f}\n")
+
+
+def parity(dst: Path):
+    rep = json.loads((SRC / "parity_report.json").read_text())
+    with open(dst, "w") as f:
+        f.write("# worst |gpu-oracle| / tolerance per case and mode (tolerance = 1e-12*|ref| + atol, tests/helpers.py)\n")
+        f.write("case/mode,worst_quantity,err_over_tol,max_rel_err_of_that_quantity,extras\n")
+        for tagk, r in sorted(rep.items()):
+            q = {k: v for k, v in r.items() if isinstance(v, dict)}
+            k = max(q, key=lambda x: q[x]["err_over_tol"])
+            extras = {a: b for a, b in r.items() if not isinstance(b, dict)}
+            f.write(f"{tagk},{k},{q[k]['err_over_tol']:.3g},{q[k]['max_rel']:.3g},\"{extras}\"\n")
+
+
+if (SRC / f"launches_{tag}.csv").exists():
+    launches(SRC / f"launches_{tag}.csv", OUT / f"{tag}_launches.csv")
+if (SRC / "parity_report.json").exists():
+    parity(OUT / f"{tag}_parity.csv")
+for rep in sorted(SRC.glob("prof_*.ncu-rep")):
+    cs = sys.argv[2] if len(sys.argv) > 2 else str(2097152 * 24)
+    txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep), cs], capture_output=True, text=True).stdout
+    (OUT / f"{tag}_{rep.stem}.txt").write_text(f"# ncu --set full, {rep.name}; workload scripts/prof_run.py: 2 097 152 cells x 24 steps\n" + txt)
+for b in sorted(SRC.glob("bench_*.json")):
+    try:
+        line = json.loads(b.read_text().strip().splitlines()[-1])
+        (OUT / f"{tag}_{b.stem}.json").write_text(json.dumps(line, indent=1) + "\n")
+    except Exception:
+        pass
+print(sorted(p.name for p in OUT.iterdir()))
