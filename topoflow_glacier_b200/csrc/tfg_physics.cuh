@@ -77,6 +77,36 @@ struct CellVol {  // diagnostic time integrals, :558-624, :1482-1494
   raw vol_P, vol_PR, vol_PS, vol_SM, vol_IM, P_max;
 };
 
+
+// ---- where the per-cell constants and the diagnostic integrals live during a launch ------------------------
+// RegCell keeps them in registers (strict / f32 kernels).  SmemCell keeps them in shared memory, one column per
+// thread, and reads a value where it is used: in the fast float64 kernel they would otherwise pin ~44 registers
+// for the whole time loop and hold the kernel at 3 blocks per SM.
+enum { kSaElev, kSSinLat, kSCosLat, kSNegTanLat, kSSinEq, kSCosEq, kSNegTanEq, kSDlon, kSTNoon, kSDa, kSTrs,
+       kSCB, kSSB, kSCB2, kSSB2, kSVolP, kSVolPR, kSVolPS, kSVolSM, kSVolIM, kSPmax, kSCount };
+
+template <class raw>
+struct RegCell {
+  raw v[kSCount];
+  __device__ __forceinline__ raw get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, raw x) { v[i] = x; }
+};
+
+template <class raw, int BLOCK>
+struct SmemCell {
+  unsigned base;  // shared-window address of this thread's column
+  __device__ __forceinline__ raw get(int i) const {
+    raw x;
+    if constexpr (sizeof(raw) == 8) asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(x) : "r"(base + i * BLOCK * 8));
+    else asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + i * BLOCK * 4));
+    return x;
+  }
+  __device__ __forceinline__ void set(int i, raw x) {
+    if constexpr (sizeof(raw) == 8) asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(base + i * BLOCK * 8), "d"(x));
+    else asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(base + i * BLOCK * 4), "f"(x));
+  }
+};
+
 template <class raw>
 struct StepOut {
   raw SM, IM, M_total, RH;
@@ -101,46 +131,44 @@ __device__ __forceinline__ Num<P> e_sat_mbar(const Consts<typename P::raw>& k, N
 }
 
 // The clock- and cell-dependent part of Clear_Sky_Radiation; returns K_cs.
-template <class P>
+template <class P, class Cell>
 __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
-                                            const CellStatic<typename P::raw>& s,
-                                            const CellAngles<typename P::raw>& ang, Num<P> th, Num<P> W_p,
-                                            Num<P> albedo) {
+                                            const Cell& s, Num<P> th, Num<P> W_p, Num<P> albedo) {
   using R = Num<P>;
   const R sin_d(tr.sin_decl), cos_d(tr.cos_decl), tan_d(tr.tan_decl), omega(k.omega);
   const R wt = omega * th;
   R c_wt, c_u;
   if constexpr (P::strict) {
     c_wt = ncos(wt);                                         // cos(omega*th), solar_funcs.py:282, :391
-    c_u = ncos(wt + R(s.dlon));                              // solar_funcs.py:867
+    c_u = ncos(wt + R(s.get(kSDlon)));                              // solar_funcs.py:867
   } else {
     // omega*th = A_t - B_c with A_t = omega*((clock-12)-TE) (host, per step) and B_c = omega*LC (per cell):
     // cos(A - B) = cosA cosB + sinA sinB -- two FMAs instead of a full-range cos()
     const R cA(tr.cos_hour), sA(tr.sin_hour);
-    c_wt = (cA * R(ang.cB)) + (sA * R(ang.sB));
-    c_u = (cA * R(ang.cB2)) + (sA * R(ang.sB2));
+    c_wt = (cA * R(s.get(kSCB))) + (sA * R(s.get(kSSB)));
+    c_u = (cA * R(s.get(kSCB2))) + (sA * R(s.get(kSSB2)));
   }
   // sunrise / sunset arguments, solar_funcs.py:325-326 (horizontal) and :796 (equivalent latitude)
-  const R arg_eq = nmin(nmax(R(-1.0), R(s.neg_tan_eq) * tan_d), R(1.0));
-  const R arg_h = nmin(nmax(R(-1.0), R(s.neg_tan_lat) * tan_d), R(1.0));
+  const R arg_eq = nmin(nmax(R(-1.0), R(s.get(kSNegTanEq)) * tan_d), R(1.0));
+  const R arg_h = nmin(nmax(R(-1.0), R(s.get(kSNegTanLat)) * tan_d), R(1.0));
   bool dark;
   if constexpr (P::strict) {
     // T_sr / T_ss exactly as solar_funcs.py:783-830, then the comparison of :939
     const R q_eq = nacos(arg_eq) / omega;
     const R q_h = nacos(arg_h) / omega;
-    const R T_sr = nmax((-q_eq) + R(s.t_noon), -q_h);
-    const R T_ss = nmin(q_eq + R(s.t_noon), q_h);
+    const R T_sr = nmax((-q_eq) + R(s.get(kSTNoon)), -q_h);
+    const R T_ss = nmin(q_eq + R(s.get(kSTNoon)), q_h);
     dark = (th <= T_sr) || (th >= T_ss);
   } else {
     // th <= -acos(a)/omega  or  th >= acos(a)/omega   <=>   cos(omega*th) <= a   for |omega*th| < pi;
     // outside that range both reference comparisons are true anyway (|T_sr|,|T_ss| <= 12 h).
     const R pi(3.141592653589793);
-    dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (nabs(wt) >= pi) || (nabs(wt + R(s.dlon)) >= pi);
+    dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (nabs(wt) >= pi) || (nabs(wt + R(s.get(kSDlon))) >= pi);
   }
   if (dark) return R(0.0);                                   // solar_funcs.py:940-941
 
   // Zenith_Angle solar_funcs.py:281-284
-  const R cosZ = (R(s.sin_lat) * sin_d) + ((R(s.cos_lat) * cos_d) * c_wt);
+  const R cosZ = (R(s.get(kSSinLat)) * sin_d) + ((R(s.get(kSCosLat)) * cos_d) * c_wt);
   // Optical_Air_Mass solar_funcs.py:549-568 (Kasten & Young 1989)
   R gamma, t1, t2;
   if constexpr (P::strict) {
@@ -166,8 +194,8 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   const R gam_s = (R(1.0) - nexp(a_s + (b_s * M_opt))) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
-  const R K_h = nmax(isc_e0 * (((cos_d * R(s.cos_lat)) * c_wt) + (sin_d * R(s.sin_lat))), R(0.0));
-  const R K_s = nmax(isc_e0 * (((cos_d * R(s.cos_eq)) * c_u) + (R(s.sin_eq) * sin_d)), R(0.0));
+  const R K_h = nmax(isc_e0 * (((cos_d * R(s.get(kSCosLat))) * c_wt) + (sin_d * R(s.get(kSSinLat)))), R(0.0));
+  const R K_s = nmax(isc_e0 * (((cos_d * R(s.get(kSCosEq))) * c_u) + (R(s.get(kSSinEq)) * sin_d)), R(0.0));
   const R half_gam = R(0.5) * gam_s;
   const R K_dif = half_gam * K_h;                            // :667
   const R K_glob = (tau * K_h) + K_dif;                      // :634, :683
@@ -177,11 +205,9 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
 
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
-template <class P, bool VOL, class WindowFn>
+template <class P, bool VOL, class Cell, class WindowFn>
 __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
-                                          const CellStatic<typename P::raw>& s,
-                                          const CellAngles<typename P::raw>& ang, Num<P> LC,
-                                          CellState<typename P::raw>& st, CellVol<typename P::raw>& vol,
+                                          Cell& s, Num<P> LC, CellState<typename P::raw>& st,
                                           Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
                                           WindowFn&& window_sum, StepOut<typename P::raw>& o) {
   using R = Num<P>;
@@ -190,11 +216,11 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
 
   // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
   const R T_K = T_air + LIT(kelvin, 273.15);
-  R p0 = R(k.sea_p0) * nexp(R(s.a_elev) / (R(k.r_star) * T_K));
+  R p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));
   if constexpr (P::strict) p0 = (p0 / 1000.0) * 10.0; else p0 = p0 * 0.01;
   // ---- update_P_rain :585, update_P_snow :604  (P * bool)
-  const bool is_rain = T_air > R(s.t_rs);
-  const bool is_snow = T_air <= R(s.t_rs);
+  const bool is_rain = T_air > R(s.get(kSTrs));
+  const bool is_snow = T_air <= R(s.get(kSTrs));
   R P_rain, P_snow;
   if constexpr (P::strict) {
     P_rain = Pp * R(is_rain ? 1.0 : 0.0);
@@ -204,11 +230,11 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     P_snow = sel(is_snow, Pp, R(0.0));
   }
   if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
-    const R da(s.da_m2);
-    vol.vol_P = (R(vol.vol_P) + ((Pp * da) * dt)).v;
-    vol.P_max = nmax(R(vol.P_max), Pp).v;
-    vol.vol_PR = (R(vol.vol_PR) + ((P_rain * da) * dt)).v;
-    vol.vol_PS = (R(vol.vol_PS) + ((P_snow * da) * dt)).v;
+    const R da(s.get(kSDa));
+    s.set(kSVolP, (R(s.get(kSVolP)) + ((Pp * da) * dt)).v);
+    s.set(kSPmax, nmax(R(s.get(kSPmax)), Pp).v);
+    s.set(kSVolPR, (R(s.get(kSVolPR)) + ((P_rain * da) * dt)).v);
+    s.set(kSVolPS, (R(s.get(kSVolPS)) + ((P_snow * da) * dt)).v);
   }
   // ---- vapour pressures :423-425
   const R e_sat_air = e_sat_mbar<P>(k, T_air);
@@ -261,7 +287,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if (h_snow == 0.0 && h_ice > 0.0) albedo = LIT(alb_ice, 0.3);         // :1049-1053
   if (h_snow == 0.0 && h_ice == 0.0) albedo = LIT(alb_bare, 0.15);       // :1054-1058
   // ---- update_net_shortwave_radiation :1122-1139
-  const R K_cs = clear_sky<P>(k, tr, s, ang, th, W_p, albedo);
+  const R K_cs = clear_sky<P>(k, tr, s, th, W_p, albedo);
   const R Qn_SW = K_cs * (R(1.0) - albedo);
   // ---- update_em_air :1167-1192
   R em_air;
@@ -289,7 +315,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if constexpr (P::strict) SM = zdiv(zdiv(nmax(E_in - Eccs, R(0.0)), dt), R(k.rho_lf));
   else SM = (nmax(E_in - Eccs, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf);
   SM = nmax(SM, R(0.0));
-  if constexpr (VOL) vol.vol_SM = (R(vol.vol_SM) + (((SM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1486-1487
+  if constexpr (VOL) s.set(kSVolSM, (R(s.get(kSVolSM)) + (((SM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
   h_swe = xadd(h_swe, xmul(P_snow, dt));
@@ -315,7 +341,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
   if constexpr (P::strict) IM = nmax(nmin(IM, zdiv(h_iwe, dt)), R(0.0)); else IM = nmax(nmin(IM, h_iwe * R(k.inv_dt)), R(0.0));
-  if constexpr (VOL) vol.vol_IM = (R(vol.vol_IM) + (((IM * R(s.da_m2)) * dt) * 3600.0)).v;  // :1493-1494
+  if constexpr (VOL) s.set(kSVolIM, (R(s.get(kSVolIM)) + (((IM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
   IM = zdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));

@@ -7,6 +7,8 @@
 // (examples/run_topoflow_glacier.py:64-109) around BmiTopoflowGlacier.update()
 // (bmi_topoflow_glacier.py:413-465).
 #pragma once
+#include <type_traits>
+
 #include "tfg_physics.cuh"
 #include "../../include/tfglacier.h"
 
@@ -17,6 +19,9 @@ namespace tfg {
 #endif
 #ifndef TFG_MIN_BLOCKS
 #define TFG_MIN_BLOCKS 3
+#endif
+#ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants live in shared memory, 128 registers suffice
+#define TFG_MIN_BLOCKS_LEAN 4
 #endif
 constexpr int kBlock = TFG_BLOCK;
 
@@ -74,7 +79,7 @@ __device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int
 }
 
 template <class P, bool REC, bool AGG, bool VOL>
-__global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
+__global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : TFG_MIN_BLOCKS) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
   using raw = typename P::raw;
   using R = Num<P>;
   const int64_t gid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -82,23 +87,27 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
   const int64_t c = active ? gid : p.n_cells - 1;
   const int64_t N = p.n_cells;
 
-  CellStatic<raw> s;
-  s.a_elev = __ldg(p.a_elev + c); s.sin_lat = __ldg(p.sin_lat + c); s.cos_lat = __ldg(p.cos_lat + c);
-  s.neg_tan_lat = __ldg(p.neg_tan_lat + c); s.sin_eq = __ldg(p.sin_eq + c); s.cos_eq = __ldg(p.cos_eq + c);
-  s.neg_tan_eq = __ldg(p.neg_tan_eq + c); s.dlon = __ldg(p.dlon + c); s.t_noon = __ldg(p.t_noon + c);
-  s.da_m2 = __ldg(p.da_m2 + c); s.t_rs = __ldg(p.t_rs + c);
+  // per-cell constants + diagnostic integrals: shared memory in the fast float64 kernel, registers otherwise
+  constexpr bool kSmem = P::lean;
+  __shared__ raw sm_cell[kSmem ? kSCount : 1][kBlock];
+  using Cell = typename std::conditional<kSmem, SmemCell<raw, kBlock>, RegCell<raw>>::type;
+  Cell s;
+  if constexpr (kSmem) s.base = (unsigned)__cvta_generic_to_shared(&sm_cell[0][threadIdx.x]);
+  s.set(kSaElev, __ldg(p.a_elev + c)); s.set(kSSinLat, __ldg(p.sin_lat + c)); s.set(kSCosLat, __ldg(p.cos_lat + c));
+  s.set(kSNegTanLat, __ldg(p.neg_tan_lat + c)); s.set(kSSinEq, __ldg(p.sin_eq + c)); s.set(kSCosEq, __ldg(p.cos_eq + c));
+  s.set(kSNegTanEq, __ldg(p.neg_tan_eq + c)); s.set(kSDlon, __ldg(p.dlon + c)); s.set(kSTNoon, __ldg(p.t_noon + c));
+  s.set(kSDa, __ldg(p.da_m2 + c)); s.set(kSTrs, __ldg(p.t_rs + c));
+  s.set(kSCB, 0); s.set(kSSB, 0); s.set(kSCB2, 0); s.set(kSSB2, 0);
   const R lon(__ldg(p.lon + c));
   const int tz = p.tz_idx ? (int)__ldg(p.tz_idx + c) : 0;
 
   CellState<raw> st;
   st.h_snow = p.h_snow[c]; st.h_swe = p.h_swe[c]; st.h_ice = p.h_ice[c]; st.h_iwe = p.h_iwe[c];
   st.eccs = p.eccs[c]; st.ecci = p.ecci[c]; st.albedo = p.albedo[c]; st.n_days = p.n_days[c];
-  CellVol<raw> vol = {0, 0, 0, 0, 0, 0};
   const bool have_vol = VOL && p.vol_P != nullptr;
-  if (have_vol) {
-    vol.vol_P = p.vol_P[c]; vol.vol_PR = p.vol_PR[c]; vol.vol_PS = p.vol_PS[c];
-    vol.vol_SM = p.vol_SM[c]; vol.vol_IM = p.vol_IM[c]; vol.P_max = p.P_max[c];
-  }
+  s.set(kSVolP, have_vol ? p.vol_P[c] : 0); s.set(kSVolPR, have_vol ? p.vol_PR[c] : 0);
+  s.set(kSVolPS, have_vol ? p.vol_PS[c] : 0); s.set(kSVolSM, have_vol ? p.vol_SM[c] : 0);
+  s.set(kSVolIM, have_vol ? p.vol_IM[c] : 0); s.set(kSPmax, have_vol ? p.P_max[c] : 0);
 
   const int slots = p.ring_slots;
   int slot = (int)(p.step0 % slots);
@@ -126,15 +135,16 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
       f4 = ld_stream(f + 4 * N);
   raw r_old = ring[(int64_t)slot * N];
   R LC(0.0);
-  CellAngles<raw> ang = {0, 0, 0, 0};
   auto set_zone = [&](raw gmt) {
     if constexpr (P::strict) {
       LC = ((R(gmt) * 15.0) - lon) / 15.0;  // True_Solar_Noon, solar_funcs.py:1466-1468
     } else {
       LC = ((R(gmt) * 15.0) - lon) * R(1.0 / 15.0);
       const raw B = p.k.omega * LC.v;
-      if constexpr (P::f32) { __sincosf(B, &ang.sB, &ang.cB); __sincosf(B - s.dlon, &ang.sB2, &ang.cB2); }
-      else { sincos(B, &ang.sB, &ang.cB); sincos(B - s.dlon, &ang.sB2, &ang.cB2); }
+      raw sb, cb, sb2, cb2;
+      if constexpr (P::f32) { __sincosf(B, &sb, &cb); __sincosf(B - s.get(kSDlon), &sb2, &cb2); }
+      else { sincos(B, &sb, &cb); sincos(B - s.get(kSDlon), &sb2, &cb2); }
+      s.set(kSSB, sb); s.set(kSCB, cb); s.set(kSSB2, sb2); s.set(kSCB2, cb2);
     }
   };
   raw gmt_prev = __longlong_as_double(0x7ff8000000000000ll);  // NaN: the first step always sets the zone
@@ -142,9 +152,8 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
   bool statics_sane = true;
   if constexpr (P::lean) {  // finite tables with |a_elev| < 1e3 (|elev| < 3.5 km ... 1e6 m is still fine for exp)
     auto finite = [](raw v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) != 0x7ff00000u; };
-    statics_sane = finite(s.a_elev) && fabs(s.a_elev) < 2.0e5 && finite(s.sin_lat) && finite(s.cos_lat) &&
-                   finite(s.neg_tan_lat) && finite(s.sin_eq) && finite(s.cos_eq) && finite(s.neg_tan_eq) &&
-                   finite(s.dlon) && finite(s.t_noon) && finite(s.t_rs) && finite(lon.v);
+    statics_sane = fabs(s.get(kSaElev)) < 2.0e5 && finite(lon.v);
+    for (int i = kSSinLat; i <= kSTrs; ++i) statics_sane = statics_sane && finite(s.get(i));
   }
   StepOut<raw> o;
   for (int t = 0; t < p.n_steps; ++t) {
@@ -193,13 +202,13 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
                         in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
                         (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
       if (__all_sync(0xffffffffu, sane)) {
-        cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+        cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
       } else {  // same step with libdevice functions and IEEE division: any input, reference semantics
         using S = Num<SafeF64>;
-        cell_step<SafeF64, VOL>(p.k, row, s, ang, S(LC.v), st, vol, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
+        cell_step<SafeF64, VOL>(p.k, row, s, S(LC.v), st, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
       }
     } else {
-      cell_step<P, VOL>(p.k, row, s, ang, LC, st, vol, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+      cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
     }
 
     if constexpr (REC) {
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
       if (have_agg) {
         // area-weighted basin sums (np.sum sites :567-568,:1486-1494 and the driver's `* da_m2`):
         // warp-shuffle tree when the warp sits inside one basin, one RED per warp and quantity
-        const double da = (double)s.da_m2;
+        const double da = (double)s.get(kSDa);
         double v0 = active ? (double)o.M_total * da : 0.0;
         double v1 = active ? (double)st.h_swe * da : 0.0;
         double v2 = active ? (double)st.h_iwe * da : 0.0;
@@ -260,8 +269,8 @@ __global__ void __launch_bounds__(kBlock, TFG_MIN_BLOCKS) run_kernel(const __gri
     p.eccs[c] = st.eccs; p.ecci[c] = st.ecci; p.albedo[c] = st.albedo; p.n_days[c] = st.n_days;
     p.SM[c] = o.SM; p.IM[c] = o.IM; p.M_total[c] = o.M_total; p.RH[c] = o.RH;
     if (have_vol) {
-      p.vol_P[c] = vol.vol_P; p.vol_PR[c] = vol.vol_PR; p.vol_PS[c] = vol.vol_PS;
-      p.vol_SM[c] = vol.vol_SM; p.vol_IM[c] = vol.vol_IM; p.P_max[c] = vol.P_max;
+      p.vol_P[c] = s.get(kSVolP); p.vol_PR[c] = s.get(kSVolPR); p.vol_PS[c] = s.get(kSVolPS);
+      p.vol_SM[c] = s.get(kSVolSM); p.vol_IM[c] = s.get(kSVolIM); p.P_max[c] = s.get(kSPmax);
     }
   }
 }
