@@ -13,9 +13,9 @@ namespace tfg {
 // Numeric literals of the physics, kept in __constant__ memory: as immediates every float64 literal costs two
 // UMOV instructions per use; from the constant bank it is one LDCU (often hoisted out of the time loop).
 struct LitTable {
-  double mag_a, mag_b, esat0, c90, ky_a, ky_b, ky_c, ky_nc, sa_a0, sa_a1, sa_b0, sa_b1, s_a0, s_a1, s_b0, s_b1, dew_c, dew_b, wp_a, wp_b, alb_r1, alb_r0, alb_0, alb_k, alb_ice, alb_bare, st_a, st_b, st_c, st_d, st_e, st_f, kelvin, c12, snow_thr, c3600;
+  double inv_esat0, inv_dew_a, esat10, mag_a, mag_b, esat0, c90, ky_a, ky_b, ky_c, ky_nc, sa_a0, sa_a1, sa_b0, sa_b1, s_a0, s_a1, s_b0, s_b1, dew_c, dew_b, wp_a, wp_b, alb_r1, alb_r0, alb_0, alb_k, alb_ice, alb_bare, st_a, st_b, st_c, st_d, st_e, st_f, kelvin, c12, snow_thr, c3600;
 };
-static __constant__ LitTable kLit = {17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0};
+static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.11, 17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0};
 #define LIT(field, value) (P::f32 ? Num<P>(value) : Num<P>(static_cast<typename P::raw>(kLit.field)))
 
 // host-precomputed scalars (products/ratios formed in the reference's own order)
@@ -48,6 +48,7 @@ struct Consts {
   raw rad2deg;       // 180 / pi (solar_funcs.py:550)
   raw deg2rad;       // pi / 180 (solar_funcs.py:566)
   raw inv_z0, inv_dt, inv_rho_lf;  // fast modes only: reciprocals of z0_air, dt, rho_H2O*Lf
+  raw inv_rstar, inv_p0c, kappa2;  // fast modes only: 1/R*, 1/(sea_p0*0.01), kappa^2
   int satterlund;
 };
 
@@ -214,10 +215,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R dt(k.dt);
   R h_snow(st.h_snow), h_swe(st.h_swe), h_ice(st.h_ice), h_iwe(st.h_iwe), Eccs(st.eccs), Ecci(st.ecci);
 
-  // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
   const R T_K = T_air + LIT(kelvin, 273.15);
-  R p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));
-  if constexpr (P::strict) p0 = (p0 / 1000.0) * 10.0; else p0 = p0 * 0.01;
   // ---- update_P_rain :585, update_P_snow :604  (P * bool)
   const bool is_rain = T_air > R(s.get(kSTrs));
   const bool is_snow = T_air <= R(s.get(kSTrs));
@@ -236,41 +234,80 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     s.set(kSVolPR, (R(s.get(kSVolPR)) + ((P_rain * da) * dt)).v);
     s.set(kSVolPS, (R(s.get(kSVolPS)) + ((P_snow * da) * dt)).v);
   }
-  // ---- vapour pressures :423-425
-  const R e_sat_air = e_sat_mbar<P>(k, T_air);
-  R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));     // :817
-  R e_air;                                                   // :818-821
-  if constexpr (P::strict) e_air = (e / 1000.0) * 10.0; else e_air = e * 0.01;
-  const R RH = e_air / e_sat_air;                            // :838
-  // ---- update_dew_point :888-893
-  const R log_term = nlog(divk(e_air, 6.1121));
-  const R T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
-  // ---- update_T_surf :906-911
-  const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
-  const R T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);
-  const R e_sat_surf = e_sat_mbar<P>(k, T_surf);
-  // ---- update_bulk_richardson_number :640-644
-  const R dT = T_air - T_surf;
-  const R top = R(k.gz) * dT;
-  R bot = (uz * uz) * T_K;
-  bot = sel(bot == 0.0, R(0.01), bot);
-  const R Ri = top / bot;
-  // ---- update_bulk_aero_conductance :670-733
-  R zr;
-  if constexpr (P::strict) zr = (R(k.z) - h_snow) / R(k.z0_air); else zr = (R(k.z) - h_snow) * R(k.inv_z0);
-  const R arg = R(k.kappa) / nlog(nmax(zr, R(0.01)));
-  const R Dn = uz * (arg * arg);
-  R Dh;
-  if (T_air == T_surf) Dh = Dn;
-  else if (Ri > 0.0) Dh = Dn / (R(1.0) + (R(10.0) * Ri));
-  else Dh = Dn * (R(1.0) - (R(10.0) * Ri));
-  // ---- update_sensible_heat_flux :744-745
-  const R Qh = (R(k.rho_cp_air) * Dh) * dT;
-  // ---- update_precipitable_water_content :919-920
-  const R W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);
-  // ---- update_vapor_pressure(SURFACE=True) :853 ; update_latent_heat_flux :931-934
-  const R e_surf = RH * e_sat_surf;
-  const R Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
+  R p0, e_sat_air, e_air, RH, T_dew, T_surf, e_sat_surf, dT, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, rTK;
+  if constexpr (P::lean) {
+    // Same quantities with 7 instead of 12 divisions: 1/T_K is shared, 1/p0 and RH come from exp(-x) instead of
+    // dividing by exp(x), and the aerodynamic block (:640-733) collapses into one quotient:
+    //   stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
+    //   unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
+    rTK = R(fm::rcp(T_K.v));
+    const R inv_p0 = nexp(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)) * R(k.inv_p0c);   // :551-556
+    const R t1a = (LIT(mag_a, 17.3) * T_air) / (T_air + LIT(mag_b, 237.3));                  // :788
+    const R en = nexp(-t1a);
+    const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));                             // :817
+    e_air = e * 0.01;
+    RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                                 // e_air / (6.11 exp(t1)), :838
+    const R log_term = nlog(e_air * LIT(inv_dew_a, 0.1636098885816659));                    // log(e_air / 6.1121), :892
+    T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
+    const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
+    T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);                                         // :906-911
+    e_sat_surf = e_sat_mbar<P>(k, T_surf);
+    dT = T_air - T_surf;
+    const R top = R(k.gz) * dT;                                                              // :640-644
+    R bot = (uz * uz) * T_K;
+    bot = sel(bot == 0.0, R(0.01), bot);
+    const R L = nlog(nmax((R(k.z) - h_snow) * R(k.inv_z0), R(0.01)));                        // :670
+    const bool stable = top > 0.0;
+    const R ten_top = R(10.0) * top;
+    const R num = sel(stable, bot, bot - ten_top);
+    const R den = sel(stable, bot + ten_top, bot);
+    const R uk2 = uz * R(k.kappa2);
+    const R LL = L * L;
+    Dh = (uk2 * num) / (LL * den);
+    Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
+    W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);                                 // :919-920
+    e_surf = RH * e_sat_surf;                                                                // :853
+    Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) * inv_p0);                  // :931-934
+    // only read when a caller records them (dead code otherwise)
+    p0 = R(1.0) / inv_p0; e_sat_air = LIT(esat10, 6.11) / en; Ri = top / bot; Dn = uk2 / LL;
+  } else {
+    // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
+    p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));
+    if constexpr (P::strict) p0 = (p0 / 1000.0) * 10.0; else p0 = p0 * 0.01;
+    // ---- vapour pressures :423-425
+    e_sat_air = e_sat_mbar<P>(k, T_air);
+    R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));     // :817
+    if constexpr (P::strict) e_air = (e / 1000.0) * 10.0; else e_air = e * 0.01;
+    RH = e_air / e_sat_air;                            // :838
+    // ---- update_dew_point :888-893
+    const R log_term = nlog(divk(e_air, 6.1121));
+    T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
+    // ---- update_T_surf :906-911
+    const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
+    T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);
+    e_sat_surf = e_sat_mbar<P>(k, T_surf);
+    // ---- update_bulk_richardson_number :640-644
+    dT = T_air - T_surf;
+    const R top = R(k.gz) * dT;
+    R bot = (uz * uz) * T_K;
+    bot = sel(bot == 0.0, R(0.01), bot);
+    Ri = top / bot;
+    // ---- update_bulk_aero_conductance :670-733
+    R zr;
+    if constexpr (P::strict) zr = (R(k.z) - h_snow) / R(k.z0_air); else zr = (R(k.z) - h_snow) * R(k.inv_z0);
+    const R arg = R(k.kappa) / nlog(nmax(zr, R(0.01)));
+    Dn = uz * (arg * arg);
+    if (T_air == T_surf) Dh = Dn;
+    else if (Ri > 0.0) Dh = Dn / (R(1.0) + (R(10.0) * Ri));
+    else Dh = Dn * (R(1.0) - (R(10.0) * Ri));
+    // ---- update_sensible_heat_flux :744-745
+    Qh = (R(k.rho_cp_air) * Dh) * dT;
+    // ---- update_precipitable_water_content :919-920
+    W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);
+    // ---- update_vapor_pressure(SURFACE=True) :853 ; update_latent_heat_flux :931-934
+    e_surf = RH * e_sat_surf;
+    Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
+  }
   // ---- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471
   const R solar_noon = (LIT(c12, 12.0) + LC) + R(tr.TE);
   const R th = R(tr.clock_hour) - solar_noon;
@@ -292,7 +329,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_em_air :1167-1192
   R em_air;
   if (!k.satterlund) {
-    const R x = divk(e_air, 10.0) / T_K;
+    R x;
+    if constexpr (P::lean) x = (e_air * 0.1) * rTK; else x = divk(e_air, 10.0) / T_K;
     const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
     em_air = (term1 * R(k.emis_b)) + R(k.canopy);
   } else {
