@@ -42,7 +42,15 @@ if (SRC / f"launches_{tag}.csv").exists():
     launches(SRC / f"launches_{tag}.csv", OUT / f"{tag}_launches.csv")
 if (SRC / "parity_report.json").exists():
     parity(OUT / f"{tag}_parity.csv")
-for rep in sorted(SRC.glob("prof_*.ncu-rep")):
+tcsv = SRC / f"traffic_{tag}.csv"
+if tcsv.exists():
+    rows = [r for r in csv.reader(open(tcsv)) if len(r) > 14 and r[0].isdigit()]
+    tot = sum(float(r[14]) for r in rows if r[12].startswith("dram__bytes"))
+    dur = [float(r[14]) for r in rows if r[12].startswith("gpu__time")]
+    (OUT / "traffic.json").write_text(json.dumps({
+        "f64_fast:16777216x128": tot, "_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, {tcsv.name}, one launch "
+        "of tfg::run_kernel<FastF64,0,1,1> at the bench configuration", "_kernel_ns_under_ncu": dur}, indent=1) + "\n")
+for rep in sorted(SRC.glob(f"prof_{tag}_*.ncu-rep")):
     cs = sys.argv[2] if len(sys.argv) > 2 else str(2097152 * 24)
     txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep), cs], capture_output=True, text=True).stdout
     (OUT / f"{tag}_{rep.stem}.txt").write_text(f"# ncu --set full, {rep.name}; workload scripts/prof_run.py: 2 097 152 cells x 24 steps\n" + txt)
