@@ -20,6 +20,9 @@ namespace tfg {
 #ifndef TFG_MIN_BLOCKS
 #define TFG_MIN_BLOCKS 3
 #endif
+#ifndef TFG_MIN_BLOCKS_F32
+#define TFG_MIN_BLOCKS_F32 8
+#endif
 #ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants live in shared memory, 128 registers suffice
 #define TFG_MIN_BLOCKS_LEAN 4
 #endif
@@ -79,7 +82,7 @@ __device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int
 }
 
 template <class P, bool REC, bool AGG, bool VOL>
-__global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : TFG_MIN_BLOCKS) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
+__global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f32 ? TFG_MIN_BLOCKS_F32 : TFG_MIN_BLOCKS)) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
   using raw = typename P::raw;
   using R = Num<P>;
   const int64_t gid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : TFG_MI
   const int64_t N = p.n_cells;
 
   // per-cell constants + diagnostic integrals: shared memory in the fast float64 kernel, registers otherwise
-  constexpr bool kSmem = P::lean;
+  constexpr bool kSmem = P::lean || P::f32;
   __shared__ raw sm_cell[kSmem ? kSCount : 1][kBlock];
   using Cell = typename std::conditional<kSmem, SmemCell<raw, kBlock>, RegCell<raw>>::type;
   Cell s;
