@@ -159,5 +159,18 @@ TFG_HD double atan_core(double x) {
 }
 TFG_HD double atan_f(double x) { return (fabs(x) < 1e150) ? atan_core(x) : atan(x); }
 
+// Stull (2011) wet-bulb temperature with RH as the reference feeds it (a fraction, reference
+// bmi_topoflow_glacier.py:1514-1520), for 0 <= RH <= 2:
+//   T*atan(0.151977*sqrt(RH+8.313659)) + atan(T+RH) - atan(RH-1.676331) + 0.00391838*RH^1.5*atan(0.023101*RH) - 4.86035
+// The first arctangent is a smooth function of RH on [0, 2] (direct polynomial, no sqrt), the last has a tiny
+// argument (4-term series); only the two middle ones need the general routine.
+TFG_HD double stull_wet_bulb(double T, double RH) {
+  const double a1 = horner_k<2>(kStull1, RH);
+  const double u = 0.023101 * RH, u2 = u * u;
+  const double a4 = u * fma(u2, fma(u2, fma(u2, fma(u2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
+  const double t4 = (0.00391838 * (RH * sqrt_pos(RH))) * a4;
+  return ((((T * a1) + atan_core(T + RH)) - atan_core(RH - 1.676331)) + t4) - 4.86035;
+}
+
 }  // namespace fm
 }  // namespace tfg

@@ -363,10 +363,17 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
   if (P_snow > 0.0) {
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
-    const R T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
-                     natan(RH - LIT(st_c, 1.676331))) +
-                    ((LIT(st_d, 0.00391838) * npow15(RH)) * natan(LIT(st_e, 0.023101) * RH))) -
-                   LIT(st_f, 4.86035);
+    R T_wb;
+    bool stull_fast = false;
+    if constexpr (P::lean) stull_fast = (RH >= 0.0) && (RH <= 2.0);
+    if (stull_fast) {
+      T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));
+    } else {
+      T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
+                       natan(RH - LIT(st_c, 1.676331))) +
+                      ((LIT(st_d, 0.00391838) * npow15(RH)) * natan(LIT(st_e, 0.023101) * RH))) -
+                     LIT(st_f, 4.86035);
+    }
     const R del_T = R(k.T0) - T_wb;
     Eccs = nmax((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in, R(0.0));
   }
