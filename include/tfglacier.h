@@ -165,6 +165,13 @@ TFG_API int tfg_convert_forcing(tfg_ctx* ctx, const void* raw, int raw_elem_size
 /* wait (device-side) on `stream` for an event recorded by tfg_ingest_async on another stream     */
 TFG_API int tfg_stream_wait_event(tfg_ctx* ctx, void* stream, void* event);
 
+/* ---- hydrograph post-processing ------------------------------------------------ */
+/* causal FIR along time of n_series float64 series stored [n_steps][n_series] (device):
+ * out[t][j] = sum_{k<taps} weights[k]*series[t-k][j]; with 20 taps of 0.05 this is the "mock routing"
+ * np.convolve(output_m_total, weights, "full")[:T] of examples/run_topoflow_glacier.py:129-131     */
+TFG_API int tfg_route_fir(tfg_ctx* ctx, const double* series, double* out, const double* weights, int32_t taps,
+                          int64_t n_steps, int64_t n_series, void* stream);
+
 /* ---- synthetic workloads for bench.py (SURVEY.md 8d cfg 4/5) ---------------------------------- */
 /* counter-based (Philox4x32-10) hourly forcing keyed by (seed, cell, absolute step)              */
 TFG_API int tfg_synth_forcing(tfg_ctx* ctx, void* forcing, int64_t step0, int32_t n_steps, int64_t n_cells,

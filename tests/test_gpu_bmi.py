@@ -194,3 +194,56 @@ def test_basin_aggregates_match_host_sums(cuda_device):
                 want = basin_sums_host(rec[k][t].cpu().numpy(), da_m2, basin_id, NB)
                 np.testing.assert_allclose(agg[t, :, j], want, rtol=1e-12, atol=1e-18)
         eng.close()
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path, cuda_device):
+    """state + snowfall window + step counter saved mid-run, resumed in a fresh model == uninterrupted run."""
+    import torch
+
+    case = load_case("rand64")
+    T = case["forcing"].shape[0]
+    forcing = torch.as_tensor(case["forcing"]).cuda()
+    a = make_engine(case, mode="f64_fast")
+    a.run(forcing)
+    b = make_engine(case, mode="f64_fast")
+    b.run(forcing[:20].contiguous(), 20)
+    torch.save(b.state_dict(), tmp_path / "ckpt.pt")
+    c = make_engine(case, mode="f64_fast")
+    c.load_state_dict(torch.load(tmp_path / "ckpt.pt", weights_only=False))
+    assert c.step_index == 20
+    c.run(forcing[20:].contiguous(), T - 20)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, c.state) and torch.equal(a.ring, c.ring)
+    d = make_engine(load_case("cats288"), mode="f64_fast")
+    with pytest.raises(ValueError):
+        d.load_state_dict(b.state_dict())
+    # through the BMI surface
+    m = _model(tmp_path, SAMPLE_CONFIG)
+    for name, v in zip(SET_ORDER, (0.0004, -2.0, 88000.0, 0.003, 4.0)):
+        m.set_value(name, v)
+    for _ in range(5):
+        m.update()
+    m.save_state(tmp_path / "bmi.pt")
+    n = _model(tmp_path, SAMPLE_CONFIG)
+    n.load_state(tmp_path / "bmi.pt")
+    assert n.get_current_time() == m.get_current_time() == 5 * 3600.0
+    m.update(), n.update()
+    for name in m.get_output_var_names():
+        assert m.get_value(name, np.zeros(1))[0] == n.get_value(name, np.zeros(1))[0]
+
+
+def test_mock_routing_fir_matches_numpy_convolve(cuda_device):
+    """20-tap 0.05 box filter of the reference example (examples/run_topoflow_glacier.py:129-131) on the device."""
+    import torch
+
+    case = load_case("cats288")
+    eng = make_engine(case, mode="f64_fast")
+    q = eng.run(torch.as_tensor(case["forcing"]).cuda(), record=("M_total",))["M_total"].to(torch.float64)
+    q = q * torch.as_tensor(case["statics"]["da"] * 1e6).cuda()
+    routed = eng.route_fir(q).cpu().numpy()
+    qh = q.cpu().numpy()
+    w = np.zeros(20) + 0.05
+    for j in range(qh.shape[1]):
+        want = np.convolve(qh[:, j], w, mode="full")[: qh.shape[0]]
+        np.testing.assert_allclose(routed[:, j], want, rtol=1e-13, atol=1e-18)
+    eng.close()

@@ -186,3 +186,55 @@ def test_bench_reference_arm_runs_on_cpu():
 
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+def _toy_gpkg(path):
+    import sqlite3
+
+    con = sqlite3.connect(path)
+    con.execute("create table divides (fid integer primary key, geom blob, divide_id text, toid text, type text, "
+                "ds_id real, areasqkm real, vpuid text, id text, lengthkm real, tot_drainage_areasqkm real, has_flowline int)")
+    con.execute("create table network (fid integer primary key, id text, toid text, divide_id text, areasqkm real)")
+    #   cat-1 -> nex-2 -> wb-2 -> nex-3 -> wb-3 -> nex-9 (terminal)      cat-2 -> nex-3     cat-3 -> nex-9     cat-7 -> nex-8 (other basin)
+    rows = [("cat-1", "nex-2", 10.0, 10.0, "wb-1"), ("cat-2", "nex-3", 5.0, 15.0, "wb-2"), ("cat-3", "nex-9", 2.5, 17.5, "wb-3"),
+            ("cat-7", "nex-8", 4.0, 4.0, "wb-7")]
+    for i, (d, t, a, tot, wb) in enumerate(rows):
+        con.execute("insert into divides (fid, divide_id, toid, areasqkm, id, tot_drainage_areasqkm) values (?,?,?,?,?,?)",
+                    (i + 1, d, t, a, wb, tot))
+        con.execute("insert into network (id, toid, divide_id, areasqkm) values (?,?,?,?)", (wb, t, d, a))
+    con.commit()
+    con.close()
+
+
+def test_hydrofabric_topology_and_basin_ids(tmp_path):
+    from topoflow_glacier_b200.hydrofabric import read_hydrofabric
+
+    p = tmp_path / "toy.gpkg"
+    _toy_gpkg(p)
+    h = read_hydrofabric(p)
+    assert h.divide_id == ["cat-1", "cat-2", "cat-3", "cat-7"] and h.areasqkm.sum() == 21.5
+    assert h.path_to_outlet("cat-1") == ["cat-1", "nex-2", "wb-2", "nex-3", "wb-3", "nex-9"]
+    assert h.terminal("cat-7") == "nex-8" and h.upstream_divides("nex-3") == ["cat-1", "cat-2"]
+    b, names = h.basin_ids(h.divide_id)
+    assert list(b) == [0, 0, 0, 1] and names == ["nex-9", "nex-8"]
+    b, names = h.basin_ids(["cat-1", "cat-2", "cat-3"], outlets=["nex-3"])
+    assert list(b) == [0, 0, 1] and names == ["nex-3", "nex-9"]
+    assert np.array_equal(h.area_of(["cat-2", "cat-7"]), [5.0, 4.0])
+    with pytest.raises(FileNotFoundError):
+        read_hydrofabric(tmp_path / "missing.gpkg")
+
+
+@pytest.mark.skipif(not Path("/root/reference/data/12082500.gpkg").exists(), reason="upstream checkout not present")
+def test_hydrofabric_shipped_gpkg_matches_configs():
+    """Build container only: the shipped GeoPackage gives the `da` values the yaml files carry."""
+    import yaml
+
+    from topoflow_glacier_b200.hydrofabric import read_hydrofabric
+
+    h = read_hydrofabric("/root/reference/data/12082500.gpkg")
+    assert len(h.divide_id) == 43 and abs(h.areasqkm.sum() - 361.0242) < 1e-3
+    for name in ("cat-3062784", "cat-3062920", "cat-3062924", "cat-3062927"):
+        cfg = yaml.safe_load(open(f"/root/reference/config/{name}.yaml"))
+        assert h.area_of([name])[0] == cfg["da"]
+    b, names = h.basin_ids(h.divide_id)
+    assert set(b) == {0} and len(names) == 1

@@ -209,6 +209,17 @@ class BmiTopoflowGlacier(_BmiBase):
         else:
             self.update_steps(n_steps)
 
+    # ------------------------------------------------------------------ checkpoint / resume (extension)
+    def save_state(self, path) -> None:
+        self._flush_inputs()
+        torch.save(self._engine.state_dict(), path)
+
+    def load_state(self, path) -> None:
+        self._engine.load_state_dict(torch.load(path, weights_only=False))
+        self._in_host.copy_(self._engine.inputs)
+        self._in_dirty[:] = False
+        self._out_valid = False
+
     # ------------------------------------------------------------------ time queries
     def get_start_time(self) -> float:
         return 0

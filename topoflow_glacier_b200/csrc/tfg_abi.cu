@@ -153,6 +153,19 @@ __global__ void convert_kernel(const src_t* __restrict__ in, raw* __restrict__ o
   }
 }
 
+// ---- causal box/FIR filter along time: the "mock routing" of the reference example --------------------------
+// out[t][j] = sum_{k < taps} w[k] * in[t-k][j]   (np.convolve(x, w, "full")[:T], examples/run_topoflow_glacier.py:129-131)
+__global__ void fir_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ w,
+                           int taps, int64_t T, int64_t M) {
+  const int64_t total = T * M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / M, j = i - t * M;
+    double acc = 0.0;
+    for (int k = 0; k < taps && k <= t; ++k) acc = fma(w[k], in[(t - k) * M + j], acc);
+    out[i] = acc;
+  }
+}
+
 // ---- synthetic forcing (bench only): Philox4x32-10 keyed by (seed, cell, step) ------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
@@ -372,6 +385,18 @@ int tfg_convert_forcing(tfg_ctx* x, const void* raw, int raw_elem_size, void* ou
     if (f32out) convert_kernel<float, float><<<grid, 256, 0, s>>>(r, static_cast<float*>(out), n_steps, n_cells);
     else convert_kernel<float, double><<<grid, 256, 0, s>>>(r, static_cast<double*>(out), n_steps, n_cells);
   }
+  TFG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tfg_route_fir(tfg_ctx* x, const double* series, double* out, const double* weights, int32_t taps, int64_t n_steps,
+                  int64_t n_series, void* stream) {
+  if (!x || !series || !out || !weights) return fail("tfg_route_fir: NULL argument");
+  if (taps < 1 || n_steps < 1 || n_series < 1) return fail("tfg_route_fir: empty problem");
+  TFG_CUDA(cudaSetDevice(x->device));
+  const int64_t total = n_steps * n_series;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  fir_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(series, out, weights, taps, n_steps, n_series);
   TFG_CUDA(cudaGetLastError());
   return 0;
 }

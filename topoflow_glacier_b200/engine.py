@@ -222,6 +222,40 @@ class MeltEngine:
         _lib.check(self.lib.tfg_synth_forcing(self.ctx, out.data_ptr(), step0, n_steps, self.N, elev.data_ptr(), seed,
                                               self.stream_ptr), "tfg_synth_forcing")
 
+    # ---- hydrograph routing stand-in --------------------------------------------------
+    def route_fir(self, series: torch.Tensor, weights=None) -> torch.Tensor:
+        """Causal FIR along time of float64 ``series[T, M]`` on the device; default = the reference example's
+        20-tap 0.05 box "mock routing" (reference ``examples/run_topoflow_glacier.py:129-131``)."""
+        w = torch.full((20,), 0.05, dtype=torch.float64) if weights is None else torch.as_tensor(weights, dtype=torch.float64)
+        w = w.to(self.device).contiguous()
+        x = series.to(self.device, torch.float64).contiguous()
+        x2 = x.reshape(x.shape[0], -1)
+        out = torch.empty_like(x2)
+        _lib.check(self.lib.tfg_route_fir(self.ctx, x2.data_ptr(), out.data_ptr(), w.data_ptr(), w.numel(), x2.shape[0],
+                                          x2.shape[1], self.stream_ptr), "tfg_route_fir")
+        return out.reshape(x.shape)
+
+    # ---- checkpoint / resume (SURVEY.md 8f rank 3; the reference has none, finalize() is a no-op) ---------------
+    def state_dict(self) -> dict:
+        """Everything that evolves: state block, snowfall window, inputs and the step counter (CPU tensors)."""
+        torch.cuda.synchronize(self.device)
+        return {"format": 1, "n_cells": self.N, "dtype": str(self.dtype), "mode": self.mode, "step_index": self.step_index,
+                "start": str(self.start), "dt_hours": self.dt_hours, "ring_slots": self.ring_slots,
+                "state": self.state.cpu(), "ring": self.ring.cpu(), "inputs": self.inputs.cpu()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if sd.get("format") != 1:
+            raise ValueError("unknown checkpoint format")
+        for k, mine in (("n_cells", self.N), ("dtype", str(self.dtype)), ("start", str(self.start)),
+                        ("dt_hours", self.dt_hours), ("ring_slots", self.ring_slots)):
+            if sd[k] != mine:
+                raise ValueError(f"checkpoint {k}={sd[k]!r} does not match this engine ({mine!r})")
+        self.state.copy_(sd["state"])
+        self.ring.copy_(sd["ring"])
+        self.inputs.copy_(sd["inputs"])
+        self.step_index = int(sd["step_index"])
+        self.ensure_horizon(self.step_index + 1)
+
     def close(self):
         if getattr(self, "ctx", None):
             torch.cuda.synchronize(self.device)
