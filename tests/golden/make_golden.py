@@ -28,6 +28,8 @@ Cases
 ``nosnow``      tests/integration_test.py:192-243
 ``year4``       4 catchments x 8760 synthetic hourly steps across both 2012/13 DST switches
 ``rand64``      64 random cells x 48 steps (wide parameter coverage incl. bare ground)
+``satterlund``  the four catchments with SATTERLUND: true (alternative e_sat / em_air), 96 steps
+``dt2``         the four catchments with dt = 2 h (36-slot window), 144 steps
 """
 
 from __future__ import annotations
@@ -143,6 +145,7 @@ def run_oracle(cfgs, forcing, tz="America/Los_Angeles"):
 
     cells = CellStatics.from_configs(cfgs, tz=tz)
     model = OracleModel(cells, Constants.from_mapping(cfgs[0]), start_time=cfgs[0]["start_time"], strict_pow=True)
+    assert model.dt == cfgs[0]["dt"]
     T = forcing.shape[0]
     out = {k: np.empty((T, cells.n)) for k in DUMP}
     for t in range(T):
@@ -279,6 +282,20 @@ def main():
     ref = run_reference(Bmi, cfgs, f, tmp)
     compare(ref, run_oracle(cfgs, f), "rand64")
     save("rand64", cfgs, f, ref)
+
+    # 6b. SATTERLUND switch (config-reachable alternative e_sat / em_air formulas, bmi_topoflow_glacier.py:790-796, :1182-1192)
+    cfgs = [dict(c, SATTERLUND=True) for c in shipped_configs()]
+    f = np.repeat(samp[:96, :, None], 4, axis=2)
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "satterlund")
+    save("satterlund", cfgs, f, ref, extra={"const_SATTERLUND": np.array(1)})
+
+    # 6c. dt = 2 h: 36-slot snowfall window, dt enters E_in, the melt caps and the albedo day counter
+    cfgs = [dict(c, dt=2) for c in shipped_configs()]
+    f = np.repeat(samp[:288:2, :, None], 4, axis=2)
+    ref = run_reference(Bmi, cfgs, f, tmp)
+    compare(ref, run_oracle(cfgs, f), "dt2")
+    save("dt2", cfgs, f, ref, extra={"const_dt": np.array(2)})
 
     # 7. one water year, four catchments, DST crossings
     cfgs = [dict(c, start_time="2012100100", end_time="2013093023") for c in shipped_configs()]

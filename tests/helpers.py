@@ -8,7 +8,7 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 STATIC_KEYS = ["da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow"]
-CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "year4"]
+CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "satterlund", "dt2", "year4"]
 
 # |gpu - ref| <= rtol*|ref| + atol, float64 modes (the atol of a flux is ~1e-12 x the size of
 # the terms that cancel in it, see DESIGN.md "Tolerances")
@@ -34,8 +34,12 @@ def load_case(name: str) -> dict:
     ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
     rows = z["rows"] if "rows" in z.files else None
     extra = {k: z[k] for k in z.files if k.startswith("upstream_")}
-    return {"name": name, "statics": statics, "N": N, "forcing": np.ascontiguousarray(forcing),
-            "start_time": str(z["start_time"]), "ref": ref, "rows": rows, **extra}
+    consts = {k[6:]: z[k].item() for k in z.files if k.startswith("const_")}  # non-default config values of the case
+    dt = int(consts.pop("dt", 1))
+    if "SATTERLUND" in consts:
+        consts["SATTERLUND"] = bool(consts["SATTERLUND"])
+    return {"name": name, "statics": statics, "N": N, "forcing": np.ascontiguousarray(forcing), "dt": dt,
+            "consts": consts, "start_time": str(z["start_time"]), "ref": ref, "rows": rows, **extra}
 
 
 def make_oracle(case: dict, strict_pow: bool = False, consts: dict | None = None):
@@ -43,7 +47,9 @@ def make_oracle(case: dict, strict_pow: bool = False, consts: dict | None = None
 
     s = case["statics"]
     cells = CellStatics(**{k: s[k].astype(np.float64) for k in STATIC_KEYS}, tz=["America/Los_Angeles"])
-    return OracleModel(cells, Constants(**(consts or {})), start_time=case["start_time"], strict_pow=strict_pow)
+    kw = dict(case.get("consts", {}), dt=case.get("dt", 1))
+    kw.update(consts or {})
+    return OracleModel(cells, Constants(**kw), start_time=case["start_time"], strict_pow=strict_pow)
 
 
 def default_constants() -> dict:
@@ -56,8 +62,9 @@ def make_engine(case: dict, mode: str = "f64", **kw):
     from topoflow_glacier_b200.engine import MeltEngine
 
     consts = default_constants()
+    consts.update(case.get("consts", {}))
     consts.update(kw.pop("consts", {}))
-    return MeltEngine(case["statics"], consts, case["start_time"], dt_hours=1, zones=["America/Los_Angeles"],
+    return MeltEngine(case["statics"], consts, case["start_time"], dt_hours=case.get("dt", 1), zones=["America/Los_Angeles"],
                       mode=mode, horizon_steps=case["forcing"].shape[0] + 1, **kw)
 
 

@@ -1,0 +1,73 @@
+"""GPU: size-independent properties at the BASELINE cfg-4 size (4096 x 4096 = 16 777 216 cells), where the
+oracle is too slow to run: chunking invariance, cell independence, aggregate consistency, sign constraints."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N_FULL = 4096 * 4096
+
+
+@pytest.mark.parametrize("mode", ["f64_fast"])
+def test_full_raster_properties(mode, cuda_device):
+    import torch
+
+    from topoflow_glacier_b200.config import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.synthetic import synthetic_cells
+
+    T, NB = 12, 4096
+    tabs = synthetic_cells(N_FULL, 4096, cuda_device)
+    raw = tabs.pop("raw")
+    basin = (torch.arange(N_FULL, device=cuda_device) // (N_FULL // NB)).to(torch.int32)
+    kw = dict(zones=[-8.0], mode=mode, horizon_steps=4000, device_statics=tabs)
+
+    def engine(**extra):
+        e = MeltEngine(None, default_constants(), "2012100100", **kw, **extra)
+        e.step_index = 3000  # early February: snowfall, melt-out of thin packs, day and night in 12 steps
+        return e
+
+    a = engine(basin_id=basin, n_basin=NB)
+    forcing = torch.empty(T, 5, N_FULL, dtype=a.dtype, device=cuda_device)
+    a.synth_forcing(forcing, 3000, T, raw["elev"].to(a.dtype), 99)
+    agg = torch.zeros(T, NB, 3, dtype=torch.float64, device=cuda_device)
+    rec = a.run(forcing, record=("M_total", "SM", "IM"), basin_agg=agg)
+
+    # 1. chunking invariance: T single-step launches (exact window re-sum) == one fused launch, bit for bit
+    b = engine()
+    for t in range(T):
+        b.run(forcing[t:t + 1], 1)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state) and torch.equal(a.ring, b.ring)
+    del b
+
+    # 2. cell independence: a random subset of cells run on its own reproduces its rows of the full run
+    idx = torch.randperm(N_FULL, device=cuda_device)[:4096]
+    sub = MeltEngine(None, default_constants(), "2012100100", zones=[-8.0], mode=mode, horizon_steps=4000,
+                     device_statics={k: v[idx].clone() for k, v in tabs.items()})
+    sub.step_index = 3000
+    sub.run(forcing[:, :, idx].contiguous(), T)
+    torch.cuda.synchronize()
+    assert torch.equal(sub.state, a.state[:, idx])
+
+    # 3. sign constraints of the reference test (tests/integration_test.py:123-135) at every step, every cell
+    for k in ("SM", "IM", "M_total"):
+        assert bool((rec[k] >= 0).all()), k
+    for k in ("h_snow", "h_swe", "h_ice", "h_iwe", "Eccs", "Ecci"):
+        assert bool((a.row(k) >= 0).all()), k
+    assert bool(torch.isfinite(a.state).all())
+
+    # 4. aggregates: sum over basins == sum over cells (area weighted), per step
+    da = tabs["da_m2"].to(torch.float64)
+    tot_cells = (rec["M_total"].to(torch.float64) * da).sum(dim=1)
+    tot_basins = agg[:, :, 0].sum(dim=1)
+    assert torch.allclose(tot_cells, tot_basins, rtol=1e-11, atol=0)
+    assert torch.allclose((a.row("h_swe").to(torch.float64) * da).sum(), agg[-1, :, 1].sum(), rtol=1e-11)
+
+    # 5. water balance of the snowpack over the window: h_swe(T) = h_swe(0) + sum(P_snow dt) - sum(SM dt 3600)
+    c = engine()
+    h0 = c.row("h_swe").clone()
+    r2 = c.run(forcing, record=("SM", "P_snow"))
+    lhs = c.row("h_swe")
+    rhs = h0 + r2["P_snow"].sum(dim=0) * 1.0 - r2["SM"].sum(dim=0) * 3600.0
+    assert float((lhs - rhs).abs().max()) < 1e-9
