@@ -31,7 +31,17 @@ def test_full_raster_properties(mode, cuda_device):
     forcing = torch.empty(T, 5, N_FULL, dtype=a.dtype, device=cuda_device)
     a.synth_forcing(forcing, 3000, T, raw["elev"].to(a.dtype), 99)
     agg = torch.zeros(T, NB, 3, dtype=torch.float64, device=cuda_device)
-    rec = a.run(forcing, record=("M_total", "SM", "IM"), basin_agg=agg)
+    a.run(forcing, basin_agg=agg)
+    # recorded series come from a second engine: the recording kernel is a different template instantiation, in
+    # which nvcc may contract other multiply-adds: in the fast mode it agrees to rounding, not bit for bit, and a
+    # rounding difference moves the melt-out knife edge for a few cells in 16.7 million
+    r = engine(basin_id=basin, n_basin=NB)
+    agg_r = torch.zeros(T, NB, 3, dtype=torch.float64, device=cuda_device)
+    rec = r.run(forcing, record=("M_total", "SM", "IM"), basin_agg=agg_r)
+    swe_r = r.row("h_swe").to(torch.float64).clone()
+    off = ((r.state - a.state).abs() > 1e-9 * a.state.abs() + 1e-12).any(dim=0)
+    assert float(off.float().mean()) < 2e-3, float(off.float().mean())
+    del r, off
 
     # 1. chunking invariance: T single-step launches (exact window re-sum) == one fused launch, bit for bit
     b = engine()
@@ -60,8 +70,9 @@ def test_full_raster_properties(mode, cuda_device):
     # 4. aggregates: sum over basins == sum over cells (area weighted), per step
     da = tabs["da_m2"].to(torch.float64)
     tot_cells = (rec["M_total"].to(torch.float64) * da).sum(dim=1)
-    tot_basins = agg[:, :, 0].sum(dim=1)
+    tot_basins = agg_r[:, :, 0].sum(dim=1)
     assert torch.allclose(tot_cells, tot_basins, rtol=1e-11, atol=0)
+    assert torch.allclose((swe_r * da).sum(), agg_r[-1, :, 1].sum(), rtol=1e-11)
     assert torch.allclose((a.row("h_swe").to(torch.float64) * da).sum(), agg[-1, :, 1].sum(), rtol=1e-11)
 
     # 5. water balance of the snowpack over the window: h_swe(T) = h_swe(0) + sum(P_snow dt) - sum(SM dt 3600)

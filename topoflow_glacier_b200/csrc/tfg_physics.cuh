@@ -242,11 +242,17 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     //   unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
     rTK = R(fm::rcp(T_K.v));
     const R inv_p0 = nexp(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)) * R(k.inv_p0c);   // :551-556
-    const R t1a = (LIT(mag_a, 17.3) * T_air) / (T_air + LIT(mag_b, 237.3));                  // :788
-    const R en = nexp(-t1a);
     const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));                             // :817
     e_air = e * 0.01;
-    RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                                 // e_air / (6.11 exp(t1)), :838
+    R en(1.0);
+    if (!k.satterlund) {
+      const R t1a = (LIT(mag_a, 17.3) * T_air) / (T_air + LIT(mag_b, 237.3));                // :788
+      en = nexp(-t1a);
+      RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                               // e_air / (6.11 exp(t1)), :838
+    } else {
+      e_sat_air = e_sat_mbar<P>(k, T_air);                                                   // :794-796
+      RH = e_air / e_sat_air;
+    }
     const R log_term = nlog(e_air * LIT(inv_dew_a, 0.1636098885816659));                    // log(e_air / 6.1121), :892
     T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
     const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
@@ -269,7 +275,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     e_surf = RH * e_sat_surf;                                                                // :853
     Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) * inv_p0);                  // :931-934
     // only read when a caller records them (dead code otherwise)
-    p0 = R(1.0) / inv_p0; e_sat_air = LIT(esat10, 6.11) / en; Ri = top / bot; Dn = uk2 / LL;
+    p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
+    if (!k.satterlund) e_sat_air = LIT(esat10, 6.11) / en;
   } else {
     // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
     p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));
