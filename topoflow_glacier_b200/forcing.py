@@ -118,19 +118,24 @@ class ForcingStreamer:
 
     def chunks(self, raw) -> Iterator:
         """Yield device forcing chunks ``[Tk, 5, N]`` in order; the consumer must launch its kernel on the
-        current stream before asking for the next chunk."""
+        current stream before asking for the next chunk.
+
+        ``raw`` is one host block ``[T, 6, N]`` (cut into pieces of ``chunk_steps``) or a sequence of host blocks
+        (each at most ``chunk_steps`` long) -- e.g. successive hours arriving from a met feed.  The copy of
+        piece k+1 is in flight while piece k is being computed.
+        """
         torch = self.torch
-        T = raw.shape[0]
-        starts = list(range(0, T, self.Tc))
-        if not starts:
+        if isinstance(raw, (list, tuple)):
+            pieces = list(raw)
+        else:
+            pieces = [raw[s:s + self.Tc] for s in range(0, raw.shape[0], self.Tc)]
+        if not pieces:
             return
-        sizes = {}
-        sizes[0] = self._submit(0, raw[0:self.Tc])
-        for k, s in enumerate(starts):
+        sizes = {0: self._submit(0, pieces[0])}
+        for k in range(len(pieces)):
             b = k % self.nb
-            if k + 1 < len(starts):  # prefetch the next chunk while this one computes
-                nb = (k + 1) % self.nb
-                sizes[k + 1] = self._submit(nb, raw[starts[k + 1]:starts[k + 1] + self.Tc])
+            if k + 1 < len(pieces):  # prefetch the next piece while this one computes
+                sizes[k + 1] = self._submit((k + 1) % self.nb, pieces[k + 1])
             cur = torch.cuda.current_stream(self.e.device)
             cur.wait_event(self.ready[b])
             yield self.d_out[b][:sizes[k]]
