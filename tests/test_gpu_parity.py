@@ -198,3 +198,64 @@ def test_large_random_sample_with_knife_edges(mode, cuda_device):
     assert melted > 100
     assert rep["knife_edge_cells"] <= max(5, 0.15 * melted) and singular.sum() <= 0.05 * N, rep
     assert not bad, bad
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_time_zones_and_dst_per_cell(mode, cuda_device):
+    """Cells in different zones (IANA names with DST, fixed offsets) across the March 2013 DST switch: the per-cell
+    UTC-offset table (tz_idx) reproduces the oracle's per-instance gmt_offset_hours (solar_funcs.py:1616-1637)."""
+    import torch
+
+    from helpers import default_constants
+    from oracle.np_ref import CellStatics, Constants, OracleModel
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    case = load_case("cats288")
+    s = {k: np.tile(v, 2) for k, v in case["statics"].items()}
+    s["lon"] = s["lon"] + np.array([0, 0, 0, 0, 15.0, 15.0, -30.0, 0.5])
+    zones = ["America/Los_Angeles", "America/Denver", -8.0, "Pacific/Honolulu"]
+    tz_idx = np.array([0, 0, 2, 0, 1, 1, 3, 2], dtype=np.uint8)
+    T = 120
+    forcing = np.tile(case["forcing"][:T], (1, 1, 2))
+    start = "2013030800"  # DST begins 2013-03-10 10:00 UTC in the two US zones
+    ora = OracleModel(CellStatics(**s, tz=[zones[i] for i in tz_idx]), Constants(), start, strict_pow=True)
+    keys = ("TSN_offset", "Qn_SW", "Q_sum", "M_total", "h_swe", "albedo")
+    want = ora.run(forcing, record=keys)
+    eng = MeltEngine(s, default_constants(), start, zones=zones, tz_idx=tz_idx, mode=mode, horizon_steps=T + 1)
+    got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).cuda(), record=keys).items()}
+    eng.close()
+    # solar time normally advances 1 h per step (-23 h at the daily wrap); it stalls for one step when DST begins
+    jumps = np.abs(np.diff(want["TSN_offset"], axis=0)) < 0.5
+    assert jumps[:, [0, 1, 3, 4, 5]].any(axis=0).all() and not jumps[:, [2, 7]].any()
+    for k in keys:
+        ok, ratio, dabs, drel = err_report(got[k], want[k], ATOL[k])
+        assert ok, (k, ratio, dabs, drel)
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_snowfall_window_threshold_knife_edge(mode, cuda_device):
+    """The 3-day snowfall total is steered to within ~1e-13 of the 0.03 m threshold (:1040).  The fused kernel keeps
+    an incremental sum and must fall back to the exact reference-order re-sum inside its guard band, so the
+    'days since snowfall' counter n must equal the oracle's at every step, exactly."""
+    import torch
+
+    case = load_case("cats288")
+    T, N = 400, case["N"]
+    rng = np.random.default_rng(5)
+    forcing = np.repeat(case["forcing"][:1], T, axis=0).copy()
+    forcing[:, 1] = -5.0                                    # all precipitation falls as snow
+    base = 0.03 / 72 / 20.0                                 # 72 identical entries sum to the threshold
+    forcing[:, 0] = base * (1.0 + rng.choice([-1, 1], (T, N)) * rng.uniform(0, 3e-13, (T, N)))
+    forcing[200:230, 0] = 0.0                               # a dry spell: the total drops below, then recovers
+    c2 = dict(case, forcing=forcing)
+    ora = make_oracle(c2, strict_pow=True)
+    want = ora.run(forcing, record=("n", "snow3day", "albedo"))
+    eng = make_engine(c2, mode=mode)
+    got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).cuda(), record=("n", "snow3day", "albedo")).items()}
+    eng.close()
+    near = np.abs(want["snow3day"] - 0.03) < 1e-12
+    assert near.sum() > 100, near.sum()                     # the test really sits on the knife edge
+    flips = np.diff((want["snow3day"] >= 0.03).astype(int), axis=0) != 0
+    assert flips.sum() > 20
+    assert np.array_equal(got["n"], want["n"])
+    assert np.array_equal(got["snow3day"][near], want["snow3day"][near])  # inside the band: the exact re-sum

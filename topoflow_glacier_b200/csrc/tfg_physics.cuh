@@ -3,7 +3,7 @@
 // Restates BmiTopoflowGlacier.update() (reference src/topoflow_glacier/bmi/bmi_topoflow_glacier.py:413-465)
 // and Clear_Sky_Radiation (reference src/topoflow_glacier/physics/solar_funcs.py:894-953) as a single
 // device function.  Quantities that depend on the clock only arrive in TimeRow, quantities that depend on the
-// cell only in CellStatic; both are evaluated on the host with the reference's scalar expressions.
+// cell only in the Cell accessor (RegCell / SmemCell); both are evaluated on the host with the reference's scalar expressions.
 // In StrictF64 mode every operation keeps the reference's order and association (line numbers in comments).
 #pragma once
 #include "tfg_num.cuh"
@@ -59,23 +59,8 @@ struct TimeRow {  // see tfg_time_row in include/tfglacier.h
 };
 
 template <class raw>
-struct CellStatic {
-  raw a_elev, sin_lat, cos_lat, neg_tan_lat, sin_eq, cos_eq, neg_tan_eq, dlon, t_noon, da_m2, t_rs;
-};
-
-template <class raw>
-struct CellAngles {  // fast modes: cos/sin of B = omega*LC and of B - dlon (per cell, changes only with the UTC offset)
-  raw cB, sB, cB2, sB2;
-};
-
-template <class raw>
 struct CellState {
   raw h_snow, h_swe, h_ice, h_iwe, eccs, ecci, albedo, n_days;
-};
-
-template <class raw>
-struct CellVol {  // diagnostic time integrals, :558-624, :1482-1494
-  raw vol_P, vol_PR, vol_PS, vol_SM, vol_IM, P_max;
 };
 
 
