@@ -88,7 +88,7 @@ TFG_HD double div(double a, double b) {
 }
 // sqrt(w) for w >= 0 (w below 1e-290 is treated as 1e-290): MUFU.RSQ64H seed + Newton
 TFG_HD double sqrt_pos(double w) {
-  w = fmax(w, 1e-290);
+  w = (w > 1e-290) ? w : 1e-290;
   double y;
 #if defined(__CUDA_ARCH__)
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
@@ -141,7 +141,7 @@ TFG_HD double pow_f(double x, double y) { return exp_f(y * log_f(x)); }
 // asin(x) for 0 <= x <= 1 (values slightly above 1 are clamped)
 TFG_HD double asin01(double x) {
   const bool big = x > 0.5;
-  const double w = big ? fmax(0.5 * (1.0 - x), 0.0) : x * x;
+  const double w = big ? 0.5 * (1.0 - fmin(x, 1.0)) : x * x;
   const double s = big ? sqrt_pos(w) : x;
   const double a = fma(s * w, horner_k<2>(kAsinP, w), s);
   // pi/2 = 1.5707963267948966 + 6.123233995736766e-17

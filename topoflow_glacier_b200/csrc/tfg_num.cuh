@@ -79,12 +79,30 @@ template <class P> __device__ __forceinline__ Num<P> sel(bool c, Num<P> a, Num<P
 template <class P> __device__ __forceinline__ Num<P> nmax(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>((a.v >= b.v) ? a.v : ((b.v > a.v) ? b.v : a.v + b.v));
   else if constexpr (P::f32) return Num<P>(fmaxf(a.v, b.v));
-  else return Num<P>((a.v > b.v) ? a.v : b.v);  // 3 instructions; fmax() costs 6 (NaN canonicalisation)
+  else {
+    // setp + selp (3 instructions).  Written in PTX because nvcc turns `a > b ? a : b` back into fmax(), whose
+    // NaN canonicalisation costs 6 instructions, two of them on the FP64 pipe.
+    double r;
+    asm("{ .reg .pred p; setp.gt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a.v), "d"(b.v));
+    return Num<P>(r);
+  }
 }
 template <class P> __device__ __forceinline__ Num<P> nmin(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>((a.v <= b.v) ? a.v : ((b.v < a.v) ? b.v : a.v + b.v));
   else if constexpr (P::f32) return Num<P>(fminf(a.v, b.v));
-  else return Num<P>((a.v < b.v) ? a.v : b.v);
+  else {
+    double r;
+    asm("{ .reg .pred p; setp.lt.f64 p, %1, %2; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a.v), "d"(b.v));
+    return Num<P>(r);
+  }
+}
+// max(x, 0).  Fast float64: clears the value when the sign bit is set, with integer ops only (no FP64-pipe slot).
+template <class P> __device__ __forceinline__ Num<P> relu(Num<P> a) {
+  if constexpr (P::strict || P::f32) return nmax(a, Num<P>(0.0));
+  else {
+    const int hi = __double2hiint(a.v), keep = ~(hi >> 31);
+    return Num<P>(__hiloint2double(hi & keep, __double2loint(a.v) & keep));
+  }
 }
 template <class P> __device__ __forceinline__ Num<P> nabs(Num<P> a) {
   if constexpr (P::f32) return Num<P>(fabsf(a.v)); else return Num<P>(fabs(a.v));

@@ -165,7 +165,7 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
     t2 = LIT(ky_a, 0.50572) / npow(gamma + LIT(ky_b, 6.07995), LIT(ky_c, 1.6364));
   } else {
     // elevation angle gamma = 90deg - Z = asin(cos Z), sin(gamma) = cos Z; a/(gamma+b)^c = a*exp(-c*log(gamma+b))
-    t1 = nmax(cosZ, R(0.0));
+    t1 = relu(cosZ);
     gamma = nasin01(t1) * R(k.rad2deg);
     t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(gamma + LIT(ky_b, 6.07995)));
   }
@@ -173,15 +173,15 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   // Atmospheric_Transmissivity solar_funcs.py:608-614
   const R a_sa = LIT(sa_a0, -0.1240) - (LIT(sa_a1, 0.0207) * W_p);
   const R b_sa = LIT(sa_b0, -0.0682) - (LIT(sa_b1, 0.0248) * W_p);
-  const R tau = nmin(nmax(nexp(a_sa + (b_sa * M_opt)) - R(k.dust), R(0.0)), R(1.0));
+  const R tau = nmin(relu(nexp(a_sa + (b_sa * M_opt)) - R(k.dust)), R(1.0));
   // Scattering_Attenuation solar_funcs.py:649-653
   const R a_s = LIT(s_a0, -0.0363) - (LIT(s_a1, 0.0084) * W_p);
   const R b_s = LIT(s_b0, -0.0572) - (LIT(s_b1, 0.0173) * W_p);
   const R gam_s = (R(1.0) - nexp(a_s + (b_s * M_opt))) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
-  const R K_h = nmax(isc_e0 * (((cos_d * R(s.get(kSCosLat))) * c_wt) + (sin_d * R(s.get(kSSinLat)))), R(0.0));
-  const R K_s = nmax(isc_e0 * (((cos_d * R(s.get(kSCosEq))) * c_u) + (R(s.get(kSSinEq)) * sin_d)), R(0.0));
+  const R K_h = relu(isc_e0 * (((cos_d * R(s.get(kSCosLat))) * c_wt) + (sin_d * R(s.get(kSSinLat)))));
+  const R K_s = relu(isc_e0 * (((cos_d * R(s.get(kSCosEq))) * c_u) + (R(s.get(kSSinEq)) * sin_d)));
   const R half_gam = R(0.5) * gam_s;
   const R K_dif = half_gam * K_h;                            // :667
   const R K_glob = (tau * K_h) + K_dif;                      // :634, :683
@@ -342,16 +342,16 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R previous_swe = h_swe;                              // :1571
   const R E_in = Q_sum * dt;
   R SM;
-  if constexpr (P::strict) SM = zdiv(zdiv(nmax(E_in - Eccs, R(0.0)), dt), R(k.rho_lf));
-  else SM = (nmax(E_in - Eccs, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf);
-  SM = nmax(SM, R(0.0));
+  if constexpr (P::strict) SM = zdiv(zdiv(relu(E_in - Eccs), dt), R(k.rho_lf));
+  else SM = (relu(E_in - Eccs) * R(k.inv_dt)) * R(k.inv_rho_lf);
+  SM = relu(SM);
   if constexpr (VOL) s.set(kSVolSM, (R(s.get(kSVolSM)) + (((SM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
   h_swe = xadd(h_swe, xmul(P_snow, dt));
   SM = zdiv(nmin(xmul(SM, k3600), h_swe), k3600);
   h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
-  h_swe = nmax(h_swe, R(0.0));
+  h_swe = relu(h_swe);
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
   if (P_snow > 0.0) {
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
@@ -367,29 +367,29 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
                      LIT(st_f, 4.86035);
     }
     const R del_T = R(k.T0) - T_wb;
-    Eccs = nmax((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in, R(0.0));
+    Eccs = relu((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in);
   }
   // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
   R IM;
-  if constexpr (P::strict) IM = nmax(zdiv(zdiv(nmax(E_in - Ecci, R(0.0)), dt), R(k.rho_lf)), R(0.0));
-  else IM = nmax((nmax(E_in - Ecci, R(0.0)) * R(k.inv_dt)) * R(k.inv_rho_lf), R(0.0));
+  if constexpr (P::strict) IM = relu(zdiv(zdiv(relu(E_in - Ecci), dt), R(k.rho_lf)));
+  else IM = relu((relu(E_in - Ecci) * R(k.inv_dt)) * R(k.inv_rho_lf));
   IM = sel((h_swe == 0.0) && (previous_swe == 0.0), IM, R(0.0));
-  Ecci = nmax(Ecci - E_in, R(0.0));
+  Ecci = relu(Ecci - E_in);
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
-  if constexpr (P::strict) IM = nmax(nmin(IM, zdiv(h_iwe, dt)), R(0.0)); else IM = nmax(nmin(IM, h_iwe * R(k.inv_dt)), R(0.0));
+  if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = relu(nmin(IM, h_iwe * R(k.inv_dt)));
   if constexpr (VOL) s.set(kSVolIM, (R(s.get(kSVolIM)) + (((IM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
   IM = zdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
-  h_iwe = nmax(h_iwe, R(0.0));
+  h_iwe = relu(h_iwe);
   // ---- update_combined_meltrate :1441-1445
   const R M_total = (IM + SM) + divk(P_rain, 3600.0);
   // ---- update_snow_depth :1711, update_ice_depth :1726
   h_snow = xmul(h_swe, R(k.ws_ratio));
   h_ice = xmul(h_iwe, R(k.wi_ratio));
   // ---- update_snowpack_cold_content :1552-1558
-  if (P_snow <= 0.0) Eccs = nmax(Eccs - E_in, R(0.0));
+  if (P_snow <= 0.0) Eccs = relu(Eccs - E_in);
   if (h_snow == 0.0) Eccs = R(0.0);
 
   st.h_snow = h_snow.v; st.h_swe = h_swe.v; st.h_ice = h_ice.v; st.h_iwe = h_iwe.v;
