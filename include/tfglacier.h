@@ -125,6 +125,10 @@ TFG_API const char* tfg_last_error(void);
 TFG_API int tfg_create(tfg_ctx** out, int device, int mode);
 TFG_API void tfg_destroy(tfg_ctx* ctx);
 TFG_API int tfg_mode(const tfg_ctx* ctx);
+/* tuning switches; TFG_OPT_TMA_STAGING: forcing tiles reach shared memory through cp.async.bulk + mbarrier
+ * (4 stages) instead of per-thread prefetching loads; results are bit-identical either way */
+#define TFG_OPT_TMA_STAGING 1
+TFG_API int tfg_set_option(tfg_ctx* ctx, int option, int64_t value);
 TFG_API size_t tfg_elem_size(const tfg_ctx* ctx);
 
 /* ---- binding (replaces BmiTopoflowGlacier.initialize, bmi_topoflow_glacier.py:274-411) ------- */

@@ -259,3 +259,30 @@ def test_snowfall_window_threshold_knife_edge(mode, cuda_device):
     assert flips.sum() > 20
     assert np.array_equal(got["n"], want["n"])
     assert np.array_equal(got["snow3day"][near], want["snow3day"][near])  # inside the band: the exact re-sum
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast", "f32"])
+def test_tma_staged_forcing_is_bit_identical(mode, cuda_device):
+    """Forcing tiles through cp.async.bulk + mbarrier (4 stages) == per-thread prefetching loads, bit for bit;
+    cell counts that are not a multiple of the block size fall back to the load path transparently."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    for N, T in ((128 * 37, 29), (128 * 3, 2), (1000, 9)):
+        statics, forcing = bench.synthetic_host_sample(N, T, seed=3)
+        f = torch.as_tensor(forcing).to(cuda_device, torch.float32 if mode == "f32" else torch.float64)
+        basin = (np.arange(N) // 200).astype(np.int32)
+        out = []
+        for tma in (False, True):
+            eng = MeltEngine(statics, default_constants(), "2013040100", zones=[-8.0], mode=mode, horizon_steps=T + 1,
+                             basin_id=basin, n_basin=int(basin.max()) + 1, tma_staging=tma)
+            agg = torch.zeros(T, int(basin.max()) + 1, 3, dtype=torch.float64, device=cuda_device)
+            eng.run(f, basin_agg=agg)
+            torch.cuda.synchronize()
+            out.append((eng.state.clone(), eng.ring.clone(), agg))
+            eng.close()
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+        assert torch.allclose(out[0][2], out[1][2], rtol=1e-12, atol=0)

@@ -11,6 +11,7 @@ from pathlib import Path
 F64_STRICT, F64_FAST, F32 = 0, 1, 2
 MODE_NAMES = {"f64": F64_STRICT, "f64_strict": F64_STRICT, "strict": F64_STRICT, "f64_fast": F64_FAST,
               "fast": F64_FAST, "f32": F32, "fp32": F32, "fp64": F64_STRICT}
+OPT_TMA_STAGING = 1
 N_FORCING = 5
 N_AGG = 3
 MAX_TZ = 8
@@ -62,6 +63,7 @@ PROTOTYPES = {
     "tfg_destroy": (None, [C.c_void_p]),
     "tfg_mode": (C.c_int, [C.c_void_p]),
     "tfg_elem_size": (C.c_size_t, [C.c_void_p]),
+    "tfg_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "tfg_set_constants": (C.c_int, [C.c_void_p, C.POINTER(Constants)]),
     "tfg_bind_static": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Statics)]),
     "tfg_bind_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),

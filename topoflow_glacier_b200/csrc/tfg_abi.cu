@@ -43,6 +43,7 @@ struct tfg_ctx {
   void* d_gmt = nullptr;
   int64_t n_time = 0;
   int n_tz = 1;
+  int use_tma = 0;  // forcing tiles staged by the TMA copy engine (tfg_set_option)
 };
 
 namespace {
@@ -109,6 +110,7 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
   p.ring_slots = x->c.ring_slots;
   p.n_tz = x->n_tz;
   p.exact_ring = (n_steps == 1);
+  p.use_tma = x->use_tma;
   p.forcing = static_cast<const raw*>(forcing);
 #define S(f) p.f = static_cast<const raw*>(x->s.f)
   S(a_elev); S(sin_lat); S(cos_lat); S(neg_tan_lat); S(lon); S(dlon); S(t_noon); S(da_m2);
@@ -251,6 +253,12 @@ void tfg_destroy(tfg_ctx* x) {
 
 int tfg_mode(const tfg_ctx* x) { return x ? x->mode : -1; }
 size_t tfg_elem_size(const tfg_ctx* x) { return (x && x->mode == TFG_F32) ? 4 : 8; }
+
+int tfg_set_option(tfg_ctx* x, int option, int64_t value) {
+  if (!x) return fail("tfg_set_option: NULL context");
+  if (option == TFG_OPT_TMA_STAGING) { x->use_tma = value != 0; return 0; }
+  return fail("tfg_set_option: unknown option");
+}
 
 int tfg_set_constants(tfg_ctx* x, const tfg_constants* c) {
   if (!x || !c) return fail("tfg_set_constants: NULL argument");

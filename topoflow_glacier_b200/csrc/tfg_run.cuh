@@ -31,7 +31,7 @@ constexpr int kBlock = TFG_BLOCK;
 template <class raw>
 struct RunParams {
   int64_t n_cells, step0;
-  int32_t n_steps, ring_slots, n_tz, exact_ring;
+  int32_t n_steps, ring_slots, n_tz, exact_ring, use_tma;
   const raw* forcing;
   const raw *a_elev, *sin_lat, *cos_lat, *neg_tan_lat, *lon, *sin_eq, *cos_eq, *neg_tan_eq, *dlon, *t_noon, *da_m2,
       *t_rs;
@@ -51,6 +51,38 @@ struct RunParams {
 };
 
 template <class raw> __device__ __forceinline__ raw ld_stream(const raw* p) { return __ldcs(p); }
+
+// ---- TMA bulk-copy staging of forcing tiles (cp.async.bulk + mbarrier, SASS: UBLKCP / SYNCS) -----------------
+// A block of kBlock cells needs, per timestep, five contiguous rows of kBlock elements (one per forcing).  One
+// elected thread asks the copy engine for them kStages steps ahead; the rows land in shared memory and complete
+// a "full" mbarrier; every thread reads its five values and arrives on an "empty" mbarrier so the stage can be
+// refilled.  No register staging, no per-thread address arithmetic, and the prefetch distance is kStages-1 steps.
+constexpr int kStages = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 
 // np.sum over the window in logical order (oldest first), i.e. NumPy's pairwise kernel for n <= 128:
 // eight interleaved accumulators, then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remainder.
@@ -81,7 +113,7 @@ __device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int
   return res;
 }
 
-template <class P, bool REC, bool AGG, bool VOL>
+template <class P, bool REC, bool AGG, bool VOL, bool TMA = false>
 __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f32 ? TFG_MIN_BLOCKS_F32 : TFG_MIN_BLOCKS)) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
   using raw = typename P::raw;
   using R = Num<P>;
@@ -134,8 +166,30 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
 
   const raw* f = p.forcing + c;
-  raw f0 = ld_stream(f), f1 = ld_stream(f + N), f2 = ld_stream(f + 2 * N), f3 = ld_stream(f + 3 * N),
-      f4 = ld_stream(f + 4 * N);
+  raw f0, f1, f2, f3, f4;
+  __shared__ alignas(128) raw sm_force[TMA ? kStages : 1][TFG_N_FORCING][TMA ? kBlock : 1];
+  __shared__ uint64_t bar_full[kStages], bar_empty[kStages];
+  const raw* fblock = p.forcing + (int64_t)blockIdx.x * kBlock;  // first cell of this block, step 0, variable 0
+  auto issue_stage = [&](int step_t) {  // elected thread: five row copies for timestep step_t
+    const int sg = step_t % kStages;
+    mbar_expect_tx(&bar_full[sg], (unsigned)(TFG_N_FORCING * kBlock * sizeof(raw)));
+#pragma unroll
+    for (int v = 0; v < TFG_N_FORCING; ++v)
+      bulk_g2s(&sm_force[sg][v][0], fblock + ((int64_t)step_t * TFG_N_FORCING + v) * N, (unsigned)(kBlock * sizeof(raw)),
+               &bar_full[sg]);
+  };
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kBlock); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < kStages && i < p.n_steps; ++i) issue_stage(i);
+  } else {
+    f0 = ld_stream(f); f1 = ld_stream(f + N); f2 = ld_stream(f + 2 * N); f3 = ld_stream(f + 3 * N);
+    f4 = ld_stream(f + 4 * N);
+  }
   raw r_old = ring[(int64_t)slot * N];
   R LC(0.0);
   auto set_zone = [&](raw gmt) {
@@ -160,11 +214,25 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
   StepOut<raw> o;
   for (int t = 0; t < p.n_steps; ++t) {
-    raw g0 = f0, g1 = f1, g2 = f2, g3 = f3, g4 = f4;
-    if (t + 1 < p.n_steps) {  // prefetch the next step's forcings
-      const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
-      g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
-      g4 = ld_stream(fn + 4 * N);
+    raw g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0;
+    if constexpr (TMA) {
+      const int sg = t % kStages;
+      mbar_wait(&bar_full[sg], (unsigned)((t / kStages) & 1));
+      f0 = sm_force[sg][0][threadIdx.x]; f1 = sm_force[sg][1][threadIdx.x]; f2 = sm_force[sg][2][threadIdx.x];
+      f3 = sm_force[sg][3][threadIdx.x]; f4 = sm_force[sg][4][threadIdx.x];
+      mbar_arrive(&bar_empty[sg]);
+      // refill the stage of the PREVIOUS step (most warps are past it already): prefetch distance kStages - 1
+      if (threadIdx.x == 0 && t >= 1 && t - 1 + kStages < p.n_steps) {
+        mbar_wait(&bar_empty[(t - 1) % kStages], (unsigned)(((t - 1) / kStages) & 1));
+        issue_stage(t - 1 + kStages);
+      }
+    } else {
+      g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
+      if (t + 1 < p.n_steps) {  // prefetch the next step's forcings
+        const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
+        g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
+        g4 = ld_stream(fn + 4 * N);
+      }
     }
     const int64_t step = p.step0 + t;
     const TimeRow<raw> row = p.rows[step];
@@ -262,7 +330,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         }
       }
     }
-    f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4;
+    if constexpr (!TMA) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
     r_old = r_next;
     slot = slot_next;
   }
@@ -282,7 +350,17 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
 template <class P>
 cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, bool vol, cudaStream_t stream) {
   const unsigned grid = (unsigned)((p.n_cells + kBlock - 1) / kBlock);
+  // TMA staging needs whole blocks and 16-byte aligned rows; otherwise the register-prefetch kernel runs
+  const bool tma = p.use_tma && !rec && (p.n_cells % kBlock == 0) && p.n_steps >= 2 &&
+                   ((reinterpret_cast<uintptr_t>(p.forcing) & 15) == 0) &&
+                   ((p.n_cells * sizeof(typename P::raw)) % 16 == 0);
   if (rec) run_kernel<P, true, true, true><<<grid, kBlock, 0, stream>>>(p);
+  else if (tma) {
+    if (agg && vol) run_kernel<P, false, true, true, true><<<grid, kBlock, 0, stream>>>(p);
+    else if (agg) run_kernel<P, false, true, false, true><<<grid, kBlock, 0, stream>>>(p);
+    else if (vol) run_kernel<P, false, false, true, true><<<grid, kBlock, 0, stream>>>(p);
+    else run_kernel<P, false, false, false, true><<<grid, kBlock, 0, stream>>>(p);
+  }
   else if (agg && vol) run_kernel<P, false, true, true><<<grid, kBlock, 0, stream>>>(p);
   else if (agg) run_kernel<P, false, true, false><<<grid, kBlock, 0, stream>>>(p);
   else if (vol) run_kernel<P, false, false, true><<<grid, kBlock, 0, stream>>>(p);

@@ -10,6 +10,7 @@ in ``Context`` (reference ``physics/context.py:18-71``) and in the attributes se
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterable, Mapping, Optional, Sequence
 
 import numpy as np
@@ -55,7 +56,8 @@ class MeltEngine:
     def __init__(self, cells: Mapping[str, np.ndarray], consts: Mapping[str, float], start_time, dt_hours: int = 1,
                  zones: Sequence = ("America/Los_Angeles",), tz_idx: Optional[np.ndarray] = None,
                  basin_id: Optional[np.ndarray] = None, n_basin: int = 0, mode: str = "f64", device: int = 0,
-                 horizon_steps: int = 24 * 366, diag_integrals: bool = True, device_statics: Optional[dict] = None):
+                 horizon_steps: int = 24 * 366, diag_integrals: bool = True, device_statics: Optional[dict] = None,
+                 tma_staging: Optional[bool] = None):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.mode = _lib.MODE_NAMES[mode] if isinstance(mode, str) else int(mode)
@@ -78,6 +80,10 @@ class MeltEngine:
             ctx = C.c_void_p()
             _lib.check(self.lib.tfg_create(C.byref(ctx), self.device.index, self.mode), "tfg_create")
             self.ctx = ctx
+            if tma_staging is None:
+                tma_staging = os.environ.get("TFG_TMA_STAGING", "0") == "1"
+            self.tma_staging = bool(tma_staging)
+            _lib.check(self.lib.tfg_set_option(ctx, _lib.OPT_TMA_STAGING, int(self.tma_staging)), "tfg_set_option")
             self._set_constants()
             if device_statics is not None:  # synthetic grids: tables already on the device
                 self.N = int(next(iter(device_statics.values())).numel())
