@@ -65,9 +65,8 @@ struct CellState {
 
 
 // ---- where the per-cell constants and the diagnostic integrals live during a launch ------------------------
-// RegCell keeps them in registers (strict / f32 kernels).  SmemCell keeps them in shared memory, one column per
-// thread, and reads a value where it is used: in the fast float64 kernel they would otherwise pin ~44 registers
-// for the whole time loop and hold the kernel at 3 blocks per SM.
+// SmemCell keeps them in shared memory, one column per thread, and reads a value where it is used: in registers
+// (RegCell) they pin ~44 registers for the whole time loop and hold the float64 kernels at 3 blocks per SM.
 enum { kSaElev, kSSinLat, kSCosLat, kSNegTanLat, kSSinEq, kSCosEq, kSNegTanEq, kSDlon, kSTNoon, kSDa, kSTrs,
        kSCB, kSSB, kSCB2, kSSB2, kSVolP, kSVolPR, kSVolPS, kSVolSM, kSVolIM, kSPmax, kSCount };
 

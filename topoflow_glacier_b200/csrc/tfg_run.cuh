@@ -18,7 +18,7 @@ namespace tfg {
 #define TFG_BLOCK 128
 #endif
 #ifndef TFG_MIN_BLOCKS
-#define TFG_MIN_BLOCKS 3
+#define TFG_MIN_BLOCKS 5
 #endif
 #ifndef TFG_MIN_BLOCKS_F32
 #define TFG_MIN_BLOCKS_F32 8
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   const int64_t c = active ? gid : p.n_cells - 1;
   const int64_t N = p.n_cells;
 
-  // per-cell constants + diagnostic integrals: shared memory in the fast float64 kernel, registers otherwise
-  constexpr bool kSmem = P::lean || P::f32;
+  // per-cell constants + diagnostic integrals live in shared memory (one column per thread)
+  constexpr bool kSmem = true;  // RegCell (registers) remains available for experiments
   __shared__ raw sm_cell[kSmem ? kSCount : 1][kBlock];
   using Cell = typename std::conditional<kSmem, SmemCell<raw, kBlock>, RegCell<raw>>::type;
   Cell s;
