@@ -369,6 +369,20 @@ def run_gpu_arm(args):
                 traffic = json.loads(tp.read_text()).get(f"{mode}:{n_cells}x{Tc}")
             except Exception:  # noqa: BLE001
                 traffic = None
+        # the unit that actually binds: FP64 pipe at 1 warp-instruction / 2 cycles / scheduler
+        compute = None
+        mp = ROOT / "profiles" / "kernel_mix.json"
+        if mp.exists() and mode != "f32":
+            try:
+                mix = json.loads(mp.read_text())[mode]
+                sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                ceiling = 148 * 4 * sm_hz / (2.0 * mix["fp64_warp_inst_per_warp_step"]) * 32
+                compute = {"bound": "fp64_pipe", "fp64_warp_inst_per_warp_step": mix["fp64_warp_inst_per_warp_step"],
+                           "ceiling_cell_steps_per_s": ceiling, "frac_of_ceiling": (cell_steps / (kern_ms * 1e-3)) / ceiling,
+                           "ncu_fp64_pipe_active_pct": mix["fp64_pipe_active_pct"],
+                           "ncu_issue_active_pct": mix["issue_active_pct"], "source": mix["source"]}
+            except Exception:  # noqa: BLE001
+                compute = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -381,7 +395,8 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "tfg::run_kernel",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_cell_step": es * _lib.N_FORCING,
-                         "note": "FP64-pipe bound, not HBM bound: see profiles/ and DESIGN.md"},
+                         "note": "FP64-pipe / issue bound, not HBM bound: see compute_roofline, profiles/ and DESIGN.md"},
+            "compute_roofline": compute,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "timesteps_per_step": Te, "raw_dtype": args.e2e_raw,
                     "path": "pinned host raw met -> ForcingStreamer (tfg_ingest_async + tfg_convert_forcing) -> tfg_run "

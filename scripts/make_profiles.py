@@ -54,6 +54,33 @@ for rep in sorted(SRC.glob(f"prof_{tag}_*.ncu-rep")):
     cs = sys.argv[2] if len(sys.argv) > 2 else str(2097152 * 24)
     txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep), cs], capture_output=True, text=True).stdout
     (OUT / f"{tag}_{rep.stem}.txt").write_text(f"# ncu --set full, {rep.name}; workload scripts/prof_run.py: 2 097 152 cells x 24 steps\n" + txt)
+# instruction mix of the hot kernel -> profiles/kernel_mix.json (bench.py turns it into the FP64-pipe ceiling)
+mix = {}
+for mode in ("f64_fast", "f64", "f32"):
+    rep = SRC / f"prof_{tag}_{mode}.ncu-rep"
+    if not rep.exists():
+        continue
+    src = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(src)))
+    h = rows[1]
+    iS, iE = h.index("Source"), h.index("Instructions Executed")
+    import re
+    tot = fp64 = 0
+    for r in rows[2:]:
+        mm = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", r[iS])
+        if mm:
+            tot += int(r[iE])
+            fp64 += int(r[iE]) if mm.group(1) in ("DFMA", "DMUL", "DADD", "DSETP") else 0
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    m = dict(zip(rr[0], rr[2]))
+    warp_steps = 2097152 * 24 / 32
+    mix[mode] = {"warp_inst_per_warp_step": tot / warp_steps, "fp64_warp_inst_per_warp_step": fp64 / warp_steps,
+                 "fp64_pipe_active_pct": float(m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 0)),
+                 "issue_active_pct": float(m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0)),
+                 "source": f"ncu --set full, {rep.name}, scripts/prof_run.py (2 097 152 cells x 24 steps)"}
+if mix:
+    (OUT / "kernel_mix.json").write_text(json.dumps(mix, indent=1) + "\n")
 for b in sorted(SRC.glob("bench_*.json")):
     try:
         line = json.loads(b.read_text().strip().splitlines()[-1])

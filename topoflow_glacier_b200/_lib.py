@@ -90,6 +90,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    if not LIB_PATH.exists() and not os.environ.get("TFG_LIBRARY"):
+        try:  # same image on the GPU box: nvcc is there, so a missing library can simply be built
+            from . import build as _build
+
+            _build.build()
+        except Exception:  # noqa: BLE001
+            pass
     if not LIB_PATH.exists():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m topoflow_glacier_b200.build` "
