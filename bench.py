@@ -302,6 +302,27 @@ def run_gpu_arm(args):
     cell_steps = n_cells * Tc
     value = world * cell_steps * args.steps / (dev_ms * 1e-3)
 
+    # ---- same launch on spatially coherent weather (precipitation shared by 4096 consecutive cells) --------------
+    # The headline above uses per-cell independent precipitation: the worst case for warp divergence
+    # in the snowfall branch.  Real rasters see storms that cover whole warps; report that case beside it.
+    coherent = None
+    if not args.no_coherent:
+        eng.synth_forcing(forcing, 0, Tc, elev, seed=20121001 + rank, storm_cells=4096)
+        one_step()
+        torch.cuda.synchronize()
+        ev2 = []
+        for _ in range(max(2, args.steps // 2)):
+            agg.zero()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.run(forcing, Tc, basin_agg=agg.buffer)
+            b.record()
+            ev2.append((a, b))
+        torch.cuda.synchronize()
+        ms2 = sum(a.elapsed_time(b) for a, b in ev2) / len(ev2)
+        coherent = {"cell_steps_per_s_per_gpu": cell_steps / (ms2 * 1e-3), "kernel_ms": ms2,
+                    "forcing": "as above, precipitation occurrence shared by 4096 consecutive cells"}
+
     # ---- end to end through the public API with host buffers -----------------------------------------------
     Te = args.e2e_chunk
     raw_dtype = torch.float32 if args.e2e_raw == "float32" else torch.float64
@@ -401,7 +422,7 @@ def run_gpu_arm(args):
                     "timesteps_per_step": Te, "raw_dtype": args.e2e_raw,
                     "path": "pinned host raw met -> ForcingStreamer (tfg_ingest_async + tfg_convert_forcing) -> tfg_run "
                             "-> D2H of 8 BMI outputs + basin aggregates"},
-            "gpu_launches": args.steps, "clocks": clocks, "wall_s": wall,
+            "gpu_launches": args.steps, "clocks": clocks, "wall_s": wall, "coherent_weather": coherent,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -427,6 +448,7 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-coherent", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

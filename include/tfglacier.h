@@ -177,9 +177,11 @@ TFG_API int tfg_route_fir(tfg_ctx* ctx, const double* series, double* out, const
                           int64_t n_steps, int64_t n_series, void* stream);
 
 /* ---- synthetic workloads for bench.py (SURVEY.md 8d cfg 4/5) ---------------------------------- */
-/* counter-based (Philox4x32-10) hourly forcing keyed by (seed, cell, absolute step)              */
+/* counter-based (Philox4x32-10) hourly forcing keyed by (seed, cell, absolute step); storm_cells > 1 makes
+ * `storm_cells` consecutive cells share the precipitation occurrence (spatially coherent weather), 1 = iid     */
 TFG_API int tfg_synth_forcing(tfg_ctx* ctx, void* forcing, int64_t step0, int32_t n_steps, int64_t n_cells,
-                      const void* elev_m /* dev [n_cells], context element type */, uint64_t seed, void* stream);
+                      const void* elev_m /* dev [n_cells], context element type */, uint64_t seed,
+                      int64_t storm_cells, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ ap.add_argument("--cells", type=int, default=1 << 21)
 ap.add_argument("--steps", type=int, default=16)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--agg", type=int, default=0)
+ap.add_argument("--storm", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 tabs = synthetic_cells(a.cells, 4096, dev)
@@ -20,7 +21,7 @@ eng = MeltEngine(None, default_constants(), "2012100100", zones=[-8.0], mode=a.m
                  device_statics=tabs, basin_id=basin, n_basin=4096 if a.agg else 0)
 f = torch.empty(a.steps, 5, a.cells, dtype=eng.dtype, device=dev)
 eng.step_index = 2400  # start in January: snow everywhere, mixed day/night
-eng.synth_forcing(f, 2400, a.steps, raw["elev"].to(eng.dtype), 7)
+eng.synth_forcing(f, 2400, a.steps, raw["elev"].to(eng.dtype), 7, a.storm)
 agg = torch.zeros(a.steps, 4096, 3, dtype=torch.float64, device=dev) if a.agg else None
 torch.cuda.synchronize()
 for i in range(a.launches):

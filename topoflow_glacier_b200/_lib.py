@@ -76,7 +76,7 @@ PROTOTYPES = {
     "tfg_route_fir": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                 C.c_void_p]),
     "tfg_synth_forcing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_uint64,
-                                    C.c_void_p]),
+                                    C.c_int64, C.c_void_p]),
 }
 
 import os

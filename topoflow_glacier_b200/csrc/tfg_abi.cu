@@ -185,7 +185,7 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 template <class raw>
 __global__ void synth_kernel(raw* __restrict__ out, const raw* __restrict__ elev, int64_t step0, int32_t n_steps,
-                             int64_t N, uint64_t seed) {
+                             int64_t N, uint64_t seed, int64_t storm_cells) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   const float lapse = -6.5e-3f * ((float)elev[c] - 2400.0f);
@@ -194,6 +194,12 @@ __global__ void synth_kernel(raw* __restrict__ out, const raw* __restrict__ elev
     uint32_t a[4], b[4];
     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a);
     philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)step, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), b);
+    if (storm_cells > 1) {  // precipitation occurrence shared by `storm_cells` consecutive cells (a weather system)
+      uint32_t w[4];
+      const int64_t cw = c / storm_cells;
+      philox4x32_10((uint32_t)cw, (uint32_t)(cw >> 32), (uint32_t)step, 2u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+      b[1] = w[1];
+    }
     // Box-Muller pairs
     const float r0 = sqrtf(-2.0f * __logf(u01(a[0]))), r1 = sqrtf(-2.0f * __logf(u01(a[2])));
     float s0, c0, s1, c1;
@@ -410,7 +416,7 @@ int tfg_route_fir(tfg_ctx* x, const double* series, double* out, const double* w
 }
 
 int tfg_synth_forcing(tfg_ctx* x, void* forcing, int64_t step0, int32_t n_steps, int64_t n_cells, const void* elev,
-                      uint64_t seed, void* stream) {
+                      uint64_t seed, int64_t storm_cells, void* stream) {
   if (!x || !forcing || !elev) return fail("tfg_synth_forcing: NULL argument");
   if (n_steps <= 0 || n_cells <= 0) return fail("tfg_synth_forcing: empty block");
   TFG_CUDA(cudaSetDevice(x->device));
@@ -418,10 +424,10 @@ int tfg_synth_forcing(tfg_ctx* x, void* forcing, int64_t step0, int32_t n_steps,
   const unsigned grid = (unsigned)((n_cells + 255) / 256);
   if (x->mode == TFG_F32)
     synth_kernel<float><<<grid, 256, 0, s>>>(static_cast<float*>(forcing), static_cast<const float*>(elev), step0,
-                                             n_steps, n_cells, seed);
+                                             n_steps, n_cells, seed, storm_cells);
   else
     synth_kernel<double><<<grid, 256, 0, s>>>(static_cast<double*>(forcing), static_cast<const double*>(elev), step0,
-                                              n_steps, n_cells, seed);
+                                              n_steps, n_cells, seed, storm_cells);
   TFG_CUDA(cudaGetLastError());
   return 0;
 }

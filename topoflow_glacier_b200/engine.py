@@ -224,9 +224,10 @@ class MeltEngine:
         """One literal ``update()`` from the current input block."""
         return self.run(self.inputs, 1, record=record)
 
-    def synth_forcing(self, out: torch.Tensor, step0: int, n_steps: int, elev: torch.Tensor, seed: int):
+    def synth_forcing(self, out: torch.Tensor, step0: int, n_steps: int, elev: torch.Tensor, seed: int,
+                      storm_cells: int = 1):
         _lib.check(self.lib.tfg_synth_forcing(self.ctx, out.data_ptr(), step0, n_steps, self.N, elev.data_ptr(), seed,
-                                              self.stream_ptr), "tfg_synth_forcing")
+                                              int(storm_cells), self.stream_ptr), "tfg_synth_forcing")
 
     # ---- hydrograph routing stand-in (SURVEY.md 8f rank 2) --------------------------------------------------
     def route_fir(self, series: torch.Tensor, weights=None) -> torch.Tensor:
