@@ -172,5 +172,42 @@ TFG_HD double stull_wet_bulb(double T, double RH) {
   return ((((T * a1) + atan_core(T + RH)) - atan_core(RH - 1.676331)) + t4) - 4.86035;
 }
 
+// ---- float32 counterparts (coefficients are FFMA immediates; MUFU reciprocal / rsqrt) ------------------------
+template <class T>
+TFG_HD float horner32(float x) {
+  float p = T::c(0);
+#pragma unroll
+  for (int i = 1; i < T::N; ++i) p = fmaf(p, x, T::c(i));
+  return p;
+}
+TFG_HD float rcp32(float b) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(b);
+#else
+  return 1.0f / b;
+#endif
+}
+TFG_HD float atan32(float x) {  // |x| < 1e30
+  const float ax = fabsf(x);
+  const bool inv = ax > 1.0f;
+  const float t = inv ? rcp32(ax) : ax;
+  const float a0 = t * horner32<kAtanP32>(t * t);
+  return copysignf(inv ? 1.5707963267948966f - a0 : a0, x);
+}
+TFG_HD float asin01_32(float x) {  // 0 <= x <= 1 (clamped)
+  const bool big = x > 0.5f;
+  const float w = big ? 0.5f * (1.0f - fminf(x, 1.0f)) : x * x;
+  const float s = big ? sqrtf(w) : x;
+  const float a = fmaf(s * w, horner32<kAsinP32>(w), s);
+  return big ? fmaf(-2.0f, a, 1.5707963267948966f) : a;
+}
+TFG_HD float stull_wet_bulb32(float T, float RH) {  // 0 <= RH <= 2
+  const float a1 = horner32<kStull132>(RH);
+  const float u = 0.023101f * RH;
+  const float a4 = u * fmaf(u * u, -1.0f / 3.0f, 1.0f);
+  const float t4 = (0.00391838f * (RH * sqrtf(RH))) * a4;
+  return ((((T * a1) + atan32(T + RH)) - atan32(RH - 1.676331f)) + t4) - 4.86035f;
+}
+
 }  // namespace fm
 }  // namespace tfg

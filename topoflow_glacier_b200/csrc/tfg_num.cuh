@@ -158,7 +158,7 @@ template <class P> __device__ __forceinline__ Num<P> ncos(Num<P> a) {
   if constexpr (P::f32) return Num<P>(__cosf(a.v)); else return Num<P>(cos(a.v));
 }
 template <class P> __device__ __forceinline__ Num<P> natan(Num<P> a) {
-  if constexpr (P::f32) return Num<P>(atanf(a.v));
+  if constexpr (P::f32) return Num<P>(fm::atan32(a.v));
   else if constexpr (P::lean) return Num<P>(fm::atan_core(a.v));
   else return Num<P>(atan(a.v));
 }
@@ -167,7 +167,7 @@ template <class P> __device__ __forceinline__ Num<P> nacos(Num<P> a) {
 }
 // asin(x)*(180/pi) for x in [0,1] (fast modes only): the solar elevation angle in degrees
 template <class P> __device__ __forceinline__ Num<P> nasin01(Num<P> a) {
-  if constexpr (P::f32) return Num<P>(asinf(fminf(a.v, 1.0f)));
+  if constexpr (P::f32) return Num<P>(fm::asin01_32(a.v));
   else if constexpr (P::lean) return Num<P>(fm::asin01(a.v));
   else return Num<P>(asin(fmin(a.v, 1.0)));
 }

@@ -356,9 +356,10 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
     R T_wb;
     bool stull_fast = false;
-    if constexpr (P::lean) stull_fast = (RH >= 0.0) && (RH <= 2.0);
+    if constexpr (P::lean || P::f32) stull_fast = (RH >= 0.0) && (RH <= 2.0);
     if (stull_fast) {
-      T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));
+      if constexpr (P::f32) T_wb = R(fm::stull_wet_bulb32(T_air.v, RH.v));
+      else T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));
     } else {
       T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
                        natan(RH - LIT(st_c, 1.676331))) +
