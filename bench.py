@@ -240,6 +240,7 @@ def run_gpu_arm(args):
     forcing = torch.empty(Tc, 5, n_cells, dtype=eng.dtype, device=dev)
     eng.synth_forcing(forcing, 0, Tc, elev, seed=20121001 + rank)
     agg = BasinAggregates(Tc, N_BASIN, device=dev)
+    fp64_peak = eng.measure_fp64_peak()  # DFMA microbenchmark, before the timed region
     torch.cuda.synchronize()
 
     # ---- GPU result on the CPU sample (same host-generated cells and forcing): the correctness check -----
@@ -396,9 +397,10 @@ def run_gpu_arm(args):
         if mp.exists() and mode != "f32":
             try:
                 mix = json.loads(mp.read_text())[mode]
-                sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-                ceiling = 148 * 4 * sm_hz / (2.0 * mix["fp64_warp_inst_per_warp_step"]) * 32
+                # ceiling = measured DFMA thread-ops/s / FP64 instructions per cell-step (a warp-instruction is 32 of them)
+                ceiling = fp64_peak / mix["fp64_warp_inst_per_warp_step"]
                 compute = {"bound": "fp64_pipe", "fp64_warp_inst_per_warp_step": mix["fp64_warp_inst_per_warp_step"],
+                           "fp64_peak_tflops_measured": 2 * fp64_peak / 1e12,
                            "ceiling_cell_steps_per_s": ceiling, "frac_of_ceiling": (cell_steps / (kern_ms * 1e-3)) / ceiling,
                            "ncu_fp64_pipe_active_pct": mix["fp64_pipe_active_pct"],
                            "ncu_issue_active_pct": mix["issue_active_pct"], "source": mix["source"]}

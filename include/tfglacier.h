@@ -176,6 +176,11 @@ TFG_API int tfg_stream_wait_event(tfg_ctx* ctx, void* stream, void* event);
 TFG_API int tfg_route_fir(tfg_ctx* ctx, const double* series, double* out, const double* weights, int32_t taps,
                           int64_t n_steps, int64_t n_series, void* stream);
 
+/* ---- measurement helper ---------------------------------------------------------------------- */
+/* DFMA microbenchmark (8 independent chains per thread, full chip): thread-level DFMA/s, i.e. FP64 FLOP/s / 2.
+ * bench.py divides it by the kernel's FP64 instruction count per cell-step to get the compute roofline.      */
+TFG_API int tfg_measure_fp64_peak(tfg_ctx* ctx, double* dfma_thread_ops_per_s, void* stream);
+
 /* ---- synthetic workloads for bench.py (SURVEY.md 8d cfg 4/5) ---------------------------------- */
 /* counter-based (Philox4x32-10) hourly forcing keyed by (seed, cell, absolute step); storm_cells > 1 makes
  * `storm_cells` consecutive cells share the precipitation occurrence (spatially coherent weather), 1 = iid     */

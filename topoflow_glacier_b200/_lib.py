@@ -75,6 +75,7 @@ PROTOTYPES = {
     "tfg_stream_wait_event": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tfg_route_fir": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                 C.c_void_p]),
+    "tfg_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "tfg_synth_forcing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_uint64,
                                     C.c_int64, C.c_void_p]),
 }

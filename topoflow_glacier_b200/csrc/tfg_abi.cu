@@ -168,6 +168,21 @@ __global__ void fir_kernel(const double* __restrict__ in, double* __restrict__ o
   }
 }
 
+// ---- FP64 pipe peak: what the compute roofline of the melt kernel is measured against -------------------------
+// 8 independent DFMA chains per thread, 1024 threads per SM-resident wave; reports DFMA warp-instructions / s.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;  // keep the chains alive
+}
+
 // ---- synthetic forcing (bench only): Philox4x32-10 keyed by (seed, cell, step) ------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
@@ -412,6 +427,35 @@ int tfg_route_fir(tfg_ctx* x, const double* series, double* out, const double* w
   const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   fir_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(series, out, weights, taps, n_steps, n_series);
   TFG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tfg_measure_fp64_peak(tfg_ctx* x, double* dfma_thread_ops_per_s, void* stream) {
+  if (!x || !dfma_thread_ops_per_s) return fail("tfg_measure_fp64_peak: NULL argument");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* d = nullptr;
+  TFG_CUDA(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t a, b;
+  TFG_CUDA(cudaEventCreate(&a));
+  TFG_CUDA(cudaEventCreate(&b));
+  const int iters = 4096, blocks = 148 * 8, threads = 256;
+  dfma_peak_kernel<<<blocks, threads, 0, s>>>(d, 64, 1.0);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    TFG_CUDA(cudaEventRecord(a, s));
+    dfma_peak_kernel<<<blocks, threads, 0, s>>>(d, iters, 1.0);
+    TFG_CUDA(cudaEventRecord(b, s));
+    TFG_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    TFG_CUDA(cudaEventElapsedTime(&ms, a, b));
+    best = ms < best ? ms : best;
+  }
+  TFG_CUDA(cudaGetLastError());
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *dfma_thread_ops_per_s = (double)blocks * threads * iters * 64.0 / (best * 1e-3);
   return 0;
 }
 

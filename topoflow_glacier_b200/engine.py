@@ -263,6 +263,12 @@ class MeltEngine:
         self.step_index = int(sd["step_index"])
         self.ensure_horizon(self.step_index + 1)
 
+    def measure_fp64_peak(self) -> float:
+        """Measured DFMA rate of this GPU in thread-level operations per second (x2 = FP64 FLOP/s)."""
+        v = C.c_double()
+        _lib.check(self.lib.tfg_measure_fp64_peak(self.ctx, C.byref(v), self.stream_ptr), "tfg_measure_fp64_peak")
+        return float(v.value)
+
     def close(self):
         if getattr(self, "ctx", None):
             torch.cuda.synchronize(self.device)
