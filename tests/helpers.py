@@ -73,7 +73,7 @@ def err_report(got: np.ndarray, want: np.ndarray, atol: float, rtol: float = RTO
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     both_nan = np.isnan(got) & np.isnan(want)
     diff = np.where(both_nan, 0.0, np.abs(got - want))
-    tol = rtol * np.abs(want) + atol
+    tol = np.where(both_nan, np.inf, rtol * np.abs(want) + atol)
     with np.errstate(divide="ignore", invalid="ignore"):
         ratio = np.where(diff == 0, 0.0, diff / np.where(tol > 0, tol, np.finfo(float).tiny))
         rel = np.where(diff == 0, 0.0, diff / np.maximum(np.abs(want), 1e-300))

@@ -286,3 +286,67 @@ def test_tma_staged_forcing_is_bit_identical(mode, cuda_device):
             eng.close()
         assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
         assert torch.allclose(out[0][2], out[1][2], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_extreme_and_missing_forcing(mode, cuda_device):
+    """Edge inputs: calm air (uz = 0), no precipitation, polar cold / desert heat, vanishing humidity (outside the
+    fast mode's sanity window -> its libdevice fallback), and NaN forcing (missing data) in single cells.  Finite
+    cells match the oracle; NaN appears in exactly the cells and quantities where the oracle has it."""
+    import torch
+
+    case = load_case("rand64")
+    T, N = 24, case["N"]
+    f = case["forcing"][:T].copy()
+    f[:, 4, 0] = 0.0                       # uz == 0: Richardson denominator 0 -> 0.01 (:642-643)
+    f[:, 0, 1] = 0.0                       # never any precipitation
+    f[:, 1, 2] = -88.0                     # extreme cold
+    f[:, 1, 3] = 58.0                      # extreme heat
+    f[:, 3, 4] = 3e-9                      # q below the fast path's sanity window
+    f[:, 4, 5] = 1e-120                    # denormal-ish wind
+    f[:, 2, 6] = 30000.0                   # very low surface pressure
+    f[5:, 1, 7] = np.nan                   # temperature missing from step 5 on
+    f[9, 0, 8] = np.nan                    # one missing precipitation value
+    c2 = dict(case, forcing=f)
+    keys = ("RH", "Q_sum", "M_total", "SM", "IM", "h_swe", "h_iwe", "Eccs", "albedo", "Qh")
+    want = make_oracle(c2, strict_pow=False).run(f, record=keys)
+    eng = make_engine(c2, mode=mode)
+    got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(f).cuda(), record=keys).items()}
+    eng.close()
+    mask = knife = None
+    from helpers import knife_edge_mask
+    knife = knife_edge_mask({k: np.nan_to_num(got[k]) for k in ("h_swe", "h_iwe")},
+                            {k: np.nan_to_num(want[k]) for k in ("h_swe", "h_iwe")})
+    for k in keys:
+        assert np.array_equal(np.isnan(got[k]), np.isnan(want[k])), k
+        ok, ratio, dabs, drel = err_report(got[k][~knife], want[k][~knife], ATOL[k])
+        assert ok, (k, ratio, dabs, drel)
+    assert np.isnan(want["Q_sum"][5:, 7]).all() and not np.isnan(want["Q_sum"][:5, 7]).any()
+    assert knife[-1].sum() <= 3
+
+
+def test_engine_argument_errors(cuda_device):
+    """Loud failures at the boundary: wrong dtype / shape / device, unknown record names, bad step counts."""
+    import torch
+
+    case = load_case("cats288")
+    eng = make_engine(case, mode="f64")
+    good = torch.as_tensor(case["forcing"][:4]).cuda()
+    with pytest.raises(ValueError):
+        eng.run(good.float())
+    with pytest.raises(ValueError):
+        eng.run(good.cpu())
+    with pytest.raises(ValueError):
+        eng.run(good[:, :4].contiguous(), 4)
+    with pytest.raises(ValueError):
+        eng.run(good.transpose(1, 2), 4)
+    with pytest.raises(KeyError):
+        eng.run(good, record=("no_such_quantity",))
+    with pytest.raises(RuntimeError):
+        eng.run(good, 0)
+    with pytest.raises(RuntimeError):  # aggregates requested without basin ids
+        eng.run(good, basin_agg=torch.zeros(4, 0, 3, dtype=torch.float64, device="cuda"))
+    assert eng.step_index == 0
+    eng.run(good)
+    assert eng.step_index == 4
+    eng.close()

@@ -18,10 +18,9 @@
 namespace tfg {
 
 // `lean`: use the guard-free cores of tfg_math.cuh (valid only for physically sane arguments; the kernel
-// checks the forcings of a warp each step and otherwise runs the same step under SafeF64).
+// checks the forcings and state of a warp each step and otherwise runs the same step under StrictF64).
 struct StrictF64 { using raw = double; static constexpr bool strict = true,  f32 = false, lean = false; };
 struct FastF64   { using raw = double; static constexpr bool strict = false, f32 = false, lean = true;  };
-struct SafeF64   { using raw = double; static constexpr bool strict = false, f32 = false, lean = false; };
 struct FastF32   { using raw = float;  static constexpr bool strict = false, f32 = true,  lean = false; };
 
 template <class P>

@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   };
   raw gmt_prev = __longlong_as_double(0x7ff8000000000000ll);  // NaN: the first step always sets the zone
 
-  bool statics_sane = true;
-  if constexpr (P::lean) {  // finite tables with |a_elev| < 1e3 (|elev| < 3.5 km ... 1e6 m is still fine for exp)
-    auto finite = [](raw v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) != 0x7ff00000u; };
+  bool statics_sane = true, state_ok = true;
+  auto finite = [](raw v) { return ((unsigned)__double2hiint((double)v) & 0x7ff00000u) != 0x7ff00000u; };
+  if constexpr (P::lean) {  // finite tables, |a_elev| < 2e5 (|elev| < 700 km), finite carried state
+    state_ok = finite(st.h_snow) && finite(st.h_swe) && finite(st.h_ice) && finite(st.h_iwe) && finite(st.eccs) &&
+               finite(st.ecci) && finite(st.albedo) && finite(st.n_days);
     statics_sane = fabs(s.get(kSaElev)) < 2.0e5 && finite(lon.v);
     for (int i = kSSinLat; i <= kSTrs; ++i) statics_sane = statics_sane && finite(s.get(i));
   }
@@ -272,11 +274,16 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
                         (((unsigned)__double2hiint(f1) & 0x7fffffffu) < (unsigned)__double2hiint(90.0)) &&
                         in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
                         (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
-      if (__all_sync(0xffffffffu, sane)) {
+      if (__all_sync(0xffffffffu, sane && state_ok)) {
         cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
-      } else {  // same step with libdevice functions and IEEE division: any input, reference semantics
-        using S = Num<SafeF64>;
-        cell_step<SafeF64, VOL>(p.k, row, s, S(LC.v), st, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
+      } else {
+        // Same step in the strict arithmetic (libdevice, IEEE division, NumPy's NaN rules): whatever the input
+        // -- missing data, absurd values -- the cell behaves like the reference, NaN poisoning included.
+        using S = Num<StrictF64>;
+        const S LCs = ((S(gmt_prev) * 15.0) - S(lon.v)) / 15.0;
+        cell_step<StrictF64, VOL>(p.k, row, s, LCs, st, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
+        state_ok = finite(st.h_snow) && finite(st.h_swe) && finite(st.h_ice) && finite(st.h_iwe) &&
+                   finite(st.eccs) && finite(st.ecci) && finite(st.albedo) && finite(st.n_days);
       }
     } else {
       cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);

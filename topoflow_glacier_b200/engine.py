@@ -210,6 +210,8 @@ class MeltEngine:
                 mask |= 1 << _lib.REC_BIT[k]
             rec_t = torch.empty(T, len(names), self.N, dtype=self.dtype, device=self.device)
         if basin_agg is not None:
+            if self.basin_id is None or self.n_basin <= 0:
+                raise RuntimeError("basin aggregates requested but the engine was built without basin_id / n_basin")
             if basin_agg.dtype != torch.float64 or basin_agg.numel() < T * self.n_basin * _lib.N_AGG:
                 raise ValueError("basin_agg must be float64 [n_steps, n_basin, 3]")
         with torch.cuda.device(self.device):
