@@ -74,7 +74,6 @@ class MeltEngine:
             raise ValueError("dt must give between 1 and 72 snowfall-window slots")
         self.step_index = 0
         self.n_basin = int(n_basin)
-        self._keep = []  # host buffers that must outlive async copies
 
         with torch.cuda.device(self.device):
             ctx = C.c_void_p()
