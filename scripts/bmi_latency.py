@@ -27,3 +27,17 @@ print("full step  %.1f us" % loop(500))
 print("sets only  %.1f us" % loop(500, True, False, False))
 print("set+update %.1f us" % loop(500, True, True, False))
 print("update+get %.1f us" % loop(500, False, True, True))
+
+# BASELINE configs[2]: the four shipped catchments as one device-resident ensemble, one water year, one launch
+import torch
+zy = np.load('tests/golden/year4.npz')
+cfgs = [dict({k: float(zy[f"static_{k}"][i]) for k in keys}, site_prefix=f"c{i}", forcing_file="-", dt=1,
+             start_time="2012100100", end_time="2013093023") for i in range(4)]
+for prec in ("f64", "f64_fast"):
+    ens = BmiTopoflowGlacier(); ens.initialize_ensemble(cfgs, mode=prec)
+    fy = torch.as_tensor(np.repeat(zy["forcing"], 4, axis=2)).cuda().contiguous()
+    ens.update_steps(24, fy[:24].contiguous()); torch.cuda.synchronize()
+    t0 = time.perf_counter(); ens.update_steps(8736, fy[24:].contiguous()); torch.cuda.synchronize()
+    dt_ = time.perf_counter() - t0
+    print(f"4-catchment ensemble, 8736 hourly steps, one launch ({prec}): {dt_*1e3:.1f} ms = {dt_/8736*1e6:.2f} us/step")
+    ens.finalize()
