@@ -1,0 +1,103 @@
+"""Attribute the SASS of one melt-kernel instantiation to lines of tfg_physics.cuh / tfg_run.cuh.
+
+    python scripts/sass_lines.py [--kernel FastF64ELb0ELb0ELb0ELb0] [--obj tfg_run_fast] [--ncu-csv FILE]
+
+Static view: `nvdisasm -gi` of the cubin inside the object file gives every instruction its inline chain; an
+instruction is booked on the outermost frame that lies in tfg_physics.cuh (else tfg_run.cuh).  With --ncu-csv (the
+`ncu -i X.ncu-rep --page source --csv` export of a capture of the SAME binary) the per-instruction "Instructions
+Executed" counts are joined by code offset, which turns the table into the dynamic instruction mix per source line.
+"""
+from __future__ import annotations
+
+import argparse
+import collections
+import csv
+import re
+import subprocess
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+FP64 = ("DFMA", "DMUL", "DADD", "DSETP", "MUFU.RCP64H", "MUFU.RSQ64H", "F2F.F64", "I2F.F64", "F2I.F64", "DMNMX")
+
+
+def disasm(obj: str) -> str:
+    o = ROOT / "topoflow_glacier_b200" / "lib" / "obj" / f"{obj}.o"
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run(["cuobjdump", "-xelf", "all", str(o)], cwd=d, check=True, capture_output=True)
+        cubin = next(Path(d).glob("*.cubin"))
+        return subprocess.run(["nvdisasm", "-gi", "-c", str(cubin)], check=True, capture_output=True, text=True).stdout
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kernel", default="FastF64ELb0ELb0ELb0ELb0")
+    ap.add_argument("--obj", default="tfg_run_fast")
+    ap.add_argument("--ncu-csv")
+    ap.add_argument("--top", type=int, default=60)
+    a = ap.parse_args()
+
+    text = disasm(a.obj)
+    sect = None
+    chain: list[tuple[str, int]] = []
+    fresh = True
+    insts = []  # (offset, opcode, booked (file, line))
+    for ln in text.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+        if m:
+            sect = m.group(1)
+            continue
+        if sect is None or a.kernel not in sect:
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            if fresh:
+                chain = []
+                fresh = False
+            chain.append((Path(m.group(1)).name, int(m.group(2))))
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
+        if m:
+            fresh = True
+            book = None
+            for f, l in reversed(chain):  # outermost first
+                if f == "tfg_physics.cuh":
+                    book = (f, l)
+                    break
+            if book is None:
+                for f, l in reversed(chain):
+                    if f == "tfg_run.cuh" and l != 278:
+                        book = (f, l)
+                        break
+            if book is None:
+                book = chain[-1] if chain else ("?", 0)
+            insts.append((int(m.group(1), 16), m.group(2), book))
+
+    dyn = None
+    if a.ncu_csv:
+        rows = list(csv.reader(open(a.ncu_csv)))
+        hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+        col = rows[hdr].index("Instructions Executed")
+        base = int(rows[hdr + 1][0], 16)
+        dyn = {int(r[0], 16) - base: int(r[col]) for r in rows[hdr + 1:] if r and r[0].startswith("0x")}
+
+    tot = collections.Counter()
+    fp = collections.Counter()
+    for off, op, book in insts:
+        w = dyn.get(off, 0) if dyn is not None else 1
+        tot[book] += w
+        if op.startswith(FP64):
+            fp[book] += w
+    all_t, all_f = sum(tot.values()), sum(fp.values())
+    src = {}
+    for f in ("tfg_physics.cuh", "tfg_run.cuh"):
+        src[f] = (ROOT / "topoflow_glacier_b200" / "csrc" / f).read_text().splitlines()
+    print(f"kernel {a.kernel}: {len(insts)} SASS instructions; {'dynamic' if dyn else 'static'} totals: all={all_t} fp64={all_f}")
+    for book, n in sorted(fp.items(), key=lambda kv: -kv[1])[: a.top]:
+        f, l = book
+        s = src.get(f, [""] * (l + 1))[l - 1].strip()[:90] if f in src else ""
+        print(f"{100 * n / max(all_f, 1):5.1f}% fp64 {n:>12} | all {tot[book]:>12} | {f}:{l}  {s}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,23 @@
+// Host build of the fast-mode elementary functions (tfg_math.cuh compiles for the host as plain C++), exported
+// as array functions so that tests/test_host_math.py can measure their error against long-double libm.
+#include "../../topoflow_glacier_b200/csrc/tfg_math.cuh"
+
+using namespace tfg::fm;
+
+#define ARRAY_FN(name, expr)                                                   \
+  extern "C" void name(const double* x, const double* y, double* out, long n) { \
+    for (long i = 0; i < n; ++i) { const double a = x[i], b = y ? y[i] : 0.0; (void)b; out[i] = (expr); } \
+  }
+ARRAY_FN(mc_exp_core, exp_core(a))
+ARRAY_FN(mc_log_core, log_core(a))
+ARRAY_FN(mc_exp_tab, exp_tab(a))
+ARRAY_FN(mc_log_tab, log_tab(a))
+ARRAY_FN(mc_rcp, rcp(a))
+ARRAY_FN(mc_rcp3, rcp3(a))
+ARRAY_FN(mc_div, div(a, b))
+ARRAY_FN(mc_div_fast, div_fast(a, b))
+ARRAY_FN(mc_sqrt_pos, sqrt_pos(a))
+ARRAY_FN(mc_asin01, asin01(a))
+ARRAY_FN(mc_atan_core, atan_core(a))
+ARRAY_FN(mc_stull, stull_wet_bulb(a, b))
+ARRAY_FN(mc_atan_diff, atan_diff(a, b))

@@ -66,13 +66,17 @@ TFG_HD double horner_k(const double (&c)[N], double x) {
   return fma(x2, fma(x, S[3], S[2]), fma(x, S[1], S[0]));
 }
 
-// 1/b for finite, normal, non-zero b: MUFU.RCP64H seed (~2^-23) + two Newton steps.
+#if !defined(__CUDA_ARCH__)
+// host stand-in for MUFU.RCP64H: reciprocal of the HIGH WORD of b (relative error up to 2^-20), low word cleared
+inline double rcp_seed_host(double b) { const double r = 1.0 / mk64(hi32(b), 0); return mk64(hi32(r), 0); }
+#endif
+// 1/b for finite, normal, non-zero b: MUFU.RCP64H seed (~2^-20) + two Newton steps.
 TFG_HD double rcp(double b) {
   double r;
 #if defined(__CUDA_ARCH__)
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
 #else
-  r = (double)(1.0f / (float)b);
+  r = rcp_seed_host(b);
 #endif
   double e = fma(-b, r, 1.0);
   r = fma(r, e, r);
@@ -86,20 +90,20 @@ TFG_HD double div(double a, double b) {
   const double q = a * r;
   return fma(fma(-b, q, a), r, q);
 }
-// sqrt(w) for w >= 0 (w below 1e-290 is treated as 1e-290): MUFU.RSQ64H seed + Newton
+// sqrt(w) for w >= 0 (w below 1e-290 is treated as 1e-290): MUFU.RSQ64H seed (~2^-20), one Newton step on
+// 1/sqrt (-> 2^-39), Heron correction (-> 2^-77)
 TFG_HD double sqrt_pos(double w) {
   w = (w > 1e-290) ? w : 1e-290;
   double y;
 #if defined(__CUDA_ARCH__)
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
 #else
-  y = (double)(1.0f / sqrtf((float)w));
+  { const double q = 1.0 / sqrt(mk64(hi32(w), 0)); y = mk64(hi32(q), 0); }  // stand-in for MUFU.RSQ64H
 #endif
-  double h = 0.5 * w;
-  y = y * fma(-h * y, y, 1.5);   // two Newton steps on 1/sqrt
+  const double h = 0.5 * w;
   y = y * fma(-h * y, y, 1.5);
-  double s = w * y;
-  return fma(fma(-s, s, w), 0.5 * y, s);  // Heron correction
+  const double s = w * y;
+  return fma(fma(-s, s, w), 0.5 * y, s);
 }
 
 // exp(x), |x| < 700
@@ -138,6 +142,72 @@ TFG_HD double log_f(double x) {
 // x**y for x > 0 (normal, finite): exp(y*log(x)); relative error ~ (|y*log x| + 2) ulp
 TFG_HD double pow_f(double x, double y) { return exp_f(y * log_f(x)); }
 
+// ---- table-driven exp / log --------------------------------------------------------------------------------
+// One lookup (64 x 8 B resp. 128 x 16 B, kept in shared memory by the melt kernel) shrinks the reduced argument
+// to |r| <= ln2/128 resp. 1/128, so a degree-5/7 polynomial replaces the degree-11/15 ones above and the log
+// needs no division: 10 resp. 13 FP64 instructions instead of 16 resp. 25, <= ~1 ulp.
+#if defined(__CUDACC__)
+extern __shared__ double tfg_tabs[];  // dynamic shared memory of the melt kernel: [0,64) 2^(j/64), [64,320) {1/c_i, log c_i}
+#endif
+#if defined(__CUDA_ARCH__)
+#define TFG_EXPTAB(j) tfg_tabs[j]
+#define TFG_LOGTAB(i, c) tfg_tabs[64 + 2 * (i) + (c)]
+#else
+#define TFG_EXPTAB(j) kExpTab[j]
+#define TFG_LOGTAB(i, c) kLogTab[i][c]
+#endif
+constexpr int kTabDoubles = 64 + 2 * 128;
+
+// 1/b, one cubic step from the MUFU.RCP64H seed (relative error e0 <= 2^-20  ->  e0^3)
+TFG_HD double rcp3(double b) {
+  double r;
+#if defined(__CUDA_ARCH__)
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#else
+  r = rcp_seed_host(b);
+#endif
+  const double e = fma(-b, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+// a/b without the final residual correction (<= ~1.5 ulp)
+TFG_HD double div_fast(double a, double b) { return a * rcp3(b); }
+
+// exp(x), |x| < 700
+TFG_HD double exp_tab(double x) {
+  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);  // low word = rint(x * 64/ln2)
+  const int k = lo32(t);
+  const double fn = t - 6755399441055744.0;
+  double r = fma(fn, -1.08304246932675596327e-02, x);   // -ln2hi/64 (32 significant bits)
+  r = fma(fn, -2.98158582698529328128e-12, r);          // -ln2lo/64
+  const double T = TFG_EXPTAB(k & 63);
+  const double r2 = r * r;
+  const double a = fma(r, TFG_COEF(kExpTQ, 2), TFG_COEF(kExpTQ, 3));
+  const double b = fma(r, TFG_COEF(kExpTQ, 0), TFG_COEF(kExpTQ, 1));
+  const double p = fma(r2, fma(r2, b, a), r);           // exp(r) - 1
+  const double y = fma(T, p, T);                        // in [1, 2.01)
+  return mk64(hi32(y) + ((k >> 6) << 20), lo32(y));
+}
+
+// log(x) for positive, normal, finite x
+TFG_HD double log_tab(double x) {
+  const int hi = hi32(x);
+  const int tmp = hi - 0x3fe60000;                      // bits(x) - bits(0.6875): z = x / 2^e in [0.6875, 1.375)
+  const int i = (tmp >> 13) & 127;
+  const int e = tmp >> 20;
+  const double z = mk64(hi - (tmp & (int)0xfff00000), lo32(x));
+  const double invc = TFG_LOGTAB(i, 0), logc = TFG_LOGTAB(i, 1);
+  const double r = fma(z, invc, -1.0);
+  const double ed = (double)e;
+  const double w = fma(ed, 6.93147180369123816490e-01, logc);
+  const double r2 = r * r;
+  const double a0 = fma(r, TFG_COEF(kLogTA, 4), TFG_COEF(kLogTA, 5));
+  const double a1 = fma(r, TFG_COEF(kLogTA, 2), TFG_COEF(kLogTA, 3));
+  const double a2 = fma(r, TFG_COEF(kLogTA, 0), TFG_COEF(kLogTA, 1));
+  const double pa = fma(r2, fma(r2, a2, a1), a0);
+  const double lo = fma(r2, pa, fma(ed, 1.90821492927058770002e-10, r));
+  return w + lo;
+}
+
 // asin(x) for 0 <= x <= 1 (values slightly above 1 are clamped)
 TFG_HD double asin01(double x) {
   const bool big = x > 0.5;
@@ -159,17 +229,31 @@ TFG_HD double atan_core(double x) {
 }
 TFG_HD double atan_f(double x) { return (fabs(x) < 1e150) ? atan_core(x) : atan(x); }
 
+// atan(a) - atan(b) = atan2(a - b, 1 + a*b): one polynomial and one reciprocal instead of two of each.
+// |a|, |b| < 1e150; absolute error <= ~2e-16 (+ 1 ulp of the quotient where a*b ~ -1, i.e. the result ~ +-pi/2).
+TFG_HD double atan_diff(double a, double b) {
+  const double y = a - b, x = fma(a, b, 1.0);
+  const double ay = fabs(y), ax = fabs(x);
+  const bool swap = ay > ax;
+  const double hi = swap ? ay : ax, lo = swap ? ax : ay;
+  const double t = (hi > 0.0) ? lo * rcp3(hi) : 0.0;     // in [0, 1]
+  double r = t * horner_k<4>(kAtanP, t * t);
+  r = swap ? ((1.5707963267948966 - r) + 6.123233995736766e-17) : r;
+  r = (x < 0.0) ? ((3.141592653589793 - r) + 1.2246467991473532e-16) : r;
+  return copysign(r, y);
+}
+
 // Stull (2011) wet-bulb temperature with RH as the reference feeds it (a fraction, reference
 // bmi_topoflow_glacier.py:1514-1520), for 0 <= RH <= 2:
 //   T*atan(0.151977*sqrt(RH+8.313659)) + atan(T+RH) - atan(RH-1.676331) + 0.00391838*RH^1.5*atan(0.023101*RH) - 4.86035
 // The first arctangent is a smooth function of RH on [0, 2] (direct polynomial, no sqrt), the last has a tiny
-// argument (4-term series); only the two middle ones need the general routine.
+// argument (4-term series), and the two middle ones are one atan2.
 TFG_HD double stull_wet_bulb(double T, double RH) {
   const double a1 = horner_k<2>(kStull1, RH);
   const double u = 0.023101 * RH, u2 = u * u;
   const double a4 = u * fma(u2, fma(u2, fma(u2, fma(u2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
   const double t4 = (0.00391838 * (RH * sqrt_pos(RH))) * a4;
-  return ((((T * a1) + atan_core(T + RH)) - atan_core(RH - 1.676331)) + t4) - 4.86035;
+  return (((T * a1) + atan_diff(T + RH, RH - 1.676331)) + t4) - 4.86035;
 }
 
 // ---- float32 counterparts (coefficients are FFMA immediates; MUFU reciprocal / rsqrt) ------------------------

@@ -224,7 +224,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // dividing by exp(x), and the aerodynamic block (:640-733) collapses into one quotient:
     //   stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
     //   unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
-    rTK = R(fm::rcp(T_K.v));
+    rTK = R(fm::rcp3(T_K.v));
     const R inv_p0 = nexp(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)) * R(k.inv_p0c);   // :551-556
     const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));                             // :817
     e_air = e * 0.01;
@@ -348,7 +348,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
   h_swe = xadd(h_swe, xmul(P_snow, dt));
-  SM = zdiv(nmin(xmul(SM, k3600), h_swe), k3600);
+  SM = div3600(nmin(xmul(SM, k3600), h_swe));
   h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
   h_swe = relu(h_swe);
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
@@ -380,7 +380,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = relu(nmin(IM, h_iwe * R(k.inv_dt)));
   if constexpr (VOL) s.set(kSVolIM, (R(s.get(kSVolIM)) + (((IM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
-  IM = zdiv(nmin(xmul(IM, k3600), h_iwe), k3600);
+  IM = div3600(nmin(xmul(IM, k3600), h_iwe));
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
   h_iwe = relu(h_iwe);
   // ---- update_combined_meltrate :1441-1445

@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   const int64_t c = active ? gid : p.n_cells - 1;
   const int64_t N = p.n_cells;
 
+  if constexpr (P::lean) {  // lookup tables of the table-driven exp / log (tfg_math.cuh) -> dynamic shared memory
+    for (int i = threadIdx.x; i < fm::kTabDoubles; i += kBlock)
+      fm::tfg_tabs[i] = (i < 64) ? fm::kExpTab[i] : fm::kLogTab[(i - 64) >> 1][(i - 64) & 1];
+    __syncthreads();
+  }
   // per-cell constants + diagnostic integrals live in shared memory (one column per thread)
   constexpr bool kSmem = true;  // RegCell (registers) remains available for experiments
   __shared__ raw sm_cell[kSmem ? kSCount : 1][kBlock];
@@ -367,17 +372,18 @@ cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, 
   const bool tma = p.use_tma && !rec && (p.n_cells % kBlock == 0) && p.n_steps >= 2 &&
                    ((reinterpret_cast<uintptr_t>(p.forcing) & 15) == 0) &&
                    ((p.n_cells * sizeof(typename P::raw)) % 16 == 0);
-  if (rec) run_kernel<P, true, true, true><<<grid, kBlock, 0, stream>>>(p);
+  const size_t dyn = P::lean ? fm::kTabDoubles * sizeof(double) : 0;
+  if (rec) run_kernel<P, true, true, true><<<grid, kBlock, dyn, stream>>>(p);
   else if (tma) {
-    if (agg && vol) run_kernel<P, false, true, true, true><<<grid, kBlock, 0, stream>>>(p);
-    else if (agg) run_kernel<P, false, true, false, true><<<grid, kBlock, 0, stream>>>(p);
-    else if (vol) run_kernel<P, false, false, true, true><<<grid, kBlock, 0, stream>>>(p);
-    else run_kernel<P, false, false, false, true><<<grid, kBlock, 0, stream>>>(p);
+    if (agg && vol) run_kernel<P, false, true, true, true><<<grid, kBlock, dyn, stream>>>(p);
+    else if (agg) run_kernel<P, false, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
+    else if (vol) run_kernel<P, false, false, true, true><<<grid, kBlock, dyn, stream>>>(p);
+    else run_kernel<P, false, false, false, true><<<grid, kBlock, dyn, stream>>>(p);
   }
-  else if (agg && vol) run_kernel<P, false, true, true><<<grid, kBlock, 0, stream>>>(p);
-  else if (agg) run_kernel<P, false, true, false><<<grid, kBlock, 0, stream>>>(p);
-  else if (vol) run_kernel<P, false, false, true><<<grid, kBlock, 0, stream>>>(p);
-  else run_kernel<P, false, false, false><<<grid, kBlock, 0, stream>>>(p);
+  else if (agg && vol) run_kernel<P, false, true, true><<<grid, kBlock, dyn, stream>>>(p);
+  else if (agg) run_kernel<P, false, true, false><<<grid, kBlock, dyn, stream>>>(p);
+  else if (vol) run_kernel<P, false, false, true><<<grid, kBlock, dyn, stream>>>(p);
+  else run_kernel<P, false, false, false><<<grid, kBlock, dyn, stream>>>(p);
   return cudaGetLastError();
 }
 
