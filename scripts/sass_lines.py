@@ -35,9 +35,13 @@ def main() -> None:
     ap.add_argument("--obj", default="tfg_run_fast")
     ap.add_argument("--ncu-csv")
     ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--via", help="only instructions inlined through a tfg_run.cuh line containing this text")
+    ap.add_argument("--ops", action="store_true", help="also print the opcode histogram of the selected instructions")
     a = ap.parse_args()
 
     text = disasm(a.obj)
+    run_src = (ROOT / "topoflow_glacier_b200" / "csrc" / "tfg_run.cuh").read_text().splitlines()
+    via_lines = {i + 1 for i, l in enumerate(run_src) if a.via and a.via in l}
     sect = None
     chain: list[tuple[str, int]] = []
     fresh = True
@@ -59,6 +63,8 @@ def main() -> None:
         m = re.match(r"\s*/\*([0-9a-f]+)\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
         if m:
             fresh = True
+            if a.via and not any(f == "tfg_run.cuh" and l in via_lines for f, l in chain):
+                continue
             book = None
             for f, l in reversed(chain):  # outermost first
                 if f == "tfg_physics.cuh":
@@ -66,7 +72,7 @@ def main() -> None:
                     break
             if book is None:
                 for f, l in reversed(chain):
-                    if f == "tfg_run.cuh" and l != 278:
+                    if f == "tfg_run.cuh" and "cell_step<" not in run_src[l - 1]:
                         book = (f, l)
                         break
             if book is None:
@@ -83,9 +89,11 @@ def main() -> None:
 
     tot = collections.Counter()
     fp = collections.Counter()
+    ops = collections.Counter()
     for off, op, book in insts:
         w = dyn.get(off, 0) if dyn is not None else 1
         tot[book] += w
+        ops[op.split(".")[0]] += w
         if op.startswith(FP64):
             fp[book] += w
     all_t, all_f = sum(tot.values()), sum(fp.values())
@@ -97,6 +105,10 @@ def main() -> None:
         f, l = book
         s = src.get(f, [""] * (l + 1))[l - 1].strip()[:90] if f in src else ""
         print(f"{100 * n / max(all_f, 1):5.1f}% fp64 {n:>12} | all {tot[book]:>12} | {f}:{l}  {s}")
+    if a.ops:
+        print("opcodes:", ", ".join(f"{k} {v}" for k, v in ops.most_common(25)))
+
+
 
 
 if __name__ == "__main__":

@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "tfg_run.cuh"
 
@@ -38,9 +40,8 @@ struct tfg_ctx {
   tfg_statics s{};
   tfg_state st{};
   int64_t n_cells = 0;
-  // device copies of the host time tables (owned by the library)
-  void* d_rows = nullptr;
-  void* d_gmt = nullptr;
+  // host copies of the clock-only tables (owned by the library); each launch carries its rows as kernel parameters
+  std::vector<double> h_rows, h_gmt;
   int64_t n_time = 0;
   int n_tz = 1;
   int use_tma = 0;  // forcing tiles staged by the TMA copy engine (tfg_set_option)
@@ -125,8 +126,11 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
   T(h_snow); T(h_swe); T(h_ice); T(h_iwe); T(eccs); T(ecci); T(albedo); T(n_days); T(SM); T(IM); T(M_total); T(RH);
   T(vol_P); T(vol_PR); T(vol_PS); T(vol_SM); T(vol_IM); T(P_max); T(ring);
 #undef T
-  p.rows = static_cast<const tfg::TimeRow<raw>*>(x->d_rows);
-  p.gmt = static_cast<const raw*>(x->d_gmt);
+  for (int32_t t = 0; t < n_steps; ++t) {
+    const double* r = &x->h_rows[(size_t)(step0 + t) * 8];
+    p.rows[t] = tfg::TimeRow<raw>{(raw)r[0], (raw)r[1], (raw)r[2], (raw)r[3], (raw)r[4], (raw)r[5], (raw)r[6], (raw)r[7]};
+    for (int z = 0; z < x->n_tz; ++z) p.gmt[t * x->n_tz + z] = (raw)x->h_gmt[(size_t)(step0 + t) * x->n_tz + z];
+  }
   p.record = static_cast<raw*>(record);
   p.record_mask = mask;
   p.n_rec = __builtin_popcountll(mask);
@@ -267,8 +271,6 @@ int tfg_create(tfg_ctx** out, int device, int mode) {
 void tfg_destroy(tfg_ctx* x) {
   if (!x) return;
   cudaSetDevice(x->device);
-  if (x->d_rows) cudaFree(x->d_rows);
-  if (x->d_gmt) cudaFree(x->d_gmt);
   delete x;
 }
 
@@ -321,35 +323,9 @@ int tfg_bind_state(tfg_ctx* x, const tfg_state* s) {
 int tfg_bind_time(tfg_ctx* x, const tfg_time_row* rows, const double* gmt, int64_t n_steps, int n_tz, void* stream) {
   if (!x || !rows || !gmt) return fail("tfg_bind_time: NULL argument");
   if (n_steps <= 0 || n_tz < 1 || n_tz > TFG_MAX_TZ) return fail("tfg_bind_time: bad n_steps / n_tz");
-  TFG_CUDA(cudaSetDevice(x->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t es = tfg_elem_size(x);
-  void *d_rows = nullptr, *d_gmt = nullptr;
-  TFG_CUDA(cudaMalloc(&d_rows, (size_t)n_steps * 8 * es));
-  TFG_CUDA(cudaMalloc(&d_gmt, (size_t)n_steps * n_tz * es));
-  if (x->mode == TFG_F32) {
-    std::string buf((size_t)n_steps * (8 + n_tz) * sizeof(float), '\0');
-    float* fr = reinterpret_cast<float*>(&buf[0]);
-    float* fg = fr + (size_t)n_steps * 8;
-    const double* src = reinterpret_cast<const double*>(rows);
-    for (int64_t i = 0; i < n_steps * 8; ++i) fr[i] = (float)src[i];
-    for (int64_t i = 0; i < n_steps * n_tz; ++i) fg[i] = (float)gmt[i];
-    TFG_CUDA(cudaMemcpyAsync(d_rows, fr, (size_t)n_steps * 8 * es, cudaMemcpyHostToDevice, s));
-    TFG_CUDA(cudaMemcpyAsync(d_gmt, fg, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
-    TFG_CUDA(cudaStreamSynchronize(s));
-  } else {
-    TFG_CUDA(cudaMemcpyAsync(d_rows, rows, (size_t)n_steps * 8 * es, cudaMemcpyHostToDevice, s));
-    TFG_CUDA(cudaMemcpyAsync(d_gmt, gmt, (size_t)n_steps * n_tz * es, cudaMemcpyHostToDevice, s));
-    TFG_CUDA(cudaStreamSynchronize(s));
-  }
-  // kernels already queued may still read the old tables: free them only after the device drained
-  if (x->d_rows || x->d_gmt) {
-    TFG_CUDA(cudaDeviceSynchronize());
-    cudaFree(x->d_rows);
-    cudaFree(x->d_gmt);
-  }
-  x->d_rows = d_rows;
-  x->d_gmt = d_gmt;
+  (void)stream;
+  x->h_rows.assign(reinterpret_cast<const double*>(rows), reinterpret_cast<const double*>(rows) + (size_t)n_steps * 8);
+  x->h_gmt.assign(gmt, gmt + (size_t)n_steps * n_tz);
   x->n_time = n_steps;
   x->n_tz = n_tz;
   return 0;
@@ -358,7 +334,7 @@ int tfg_bind_time(tfg_ctx* x, const tfg_time_row* rows, const double* gmt, int64
 int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, void* record, uint64_t record_mask,
             double* basin_agg, int32_t n_basin, void* stream) {
   if (!x || !forcing) return fail("tfg_run: NULL argument");
-  if (!x->have_consts || !x->have_static || !x->have_state || !x->d_rows)
+  if (!x->have_consts || !x->have_static || !x->have_state || x->h_rows.empty())
     return fail("tfg_run: constants, statics, state and time tables must be bound first");
   if (n_steps <= 0 || step0 < 0) return fail("tfg_run: bad step range");
   if (step0 + n_steps > x->n_time) return fail("tfg_run: step range exceeds the bound time table");
@@ -367,14 +343,21 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
   TFG_CUDA(cudaSetDevice(x->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool rec = record != nullptr, agg = basin_agg != nullptr, vol = x->st.vol_P != nullptr;
-  cudaError_t e;
-  if (x->mode == TFG_F32) {
-    e = tfg::launch_run_f32(make_params<float>(x, forcing, step0, n_steps, record, record_mask, basin_agg, n_basin),
-                            rec, agg, vol, s);
-  } else {
-    auto p = make_params<double>(x, forcing, step0, n_steps, record, record_mask, basin_agg, n_basin);
-    e = (x->mode == TFG_F64_STRICT) ? tfg::launch_run_strict(p, rec, agg, vol, s)
-                                    : tfg::launch_run_fast(p, rec, agg, vol, s);
+  cudaError_t e = cudaSuccess;
+  const size_t es = tfg_elem_size(x);
+  // a launch carries at most kMaxLaunchSteps clock rows; longer runs are a sequence of launches on the same stream
+  // (bit-identical to one launch: state and snowfall window are carried through HBM either way)
+  for (int32_t t0 = 0; t0 < n_steps && e == cudaSuccess; t0 += tfg::kMaxLaunchSteps) {
+    const int32_t nt = std::min<int32_t>(tfg::kMaxLaunchSteps, n_steps - t0);
+    const void* f = static_cast<const char*>(forcing) + (size_t)t0 * TFG_N_FORCING * x->n_cells * es;
+    void* r = record ? static_cast<char*>(record) + (size_t)t0 * __builtin_popcountll(record_mask) * x->n_cells * es : nullptr;
+    double* a = basin_agg ? basin_agg + (size_t)t0 * n_basin * TFG_N_AGG : nullptr;
+    if (x->mode == TFG_F32) {
+      e = tfg::launch_run_f32(make_params<float>(x, f, step0 + t0, nt, r, record_mask, a, n_basin), rec, agg, vol, s);
+    } else {
+      auto p = make_params<double>(x, f, step0 + t0, nt, r, record_mask, a, n_basin);
+      e = (x->mode == TFG_F64_STRICT) ? tfg::launch_run_strict(p, rec, agg, vol, s) : tfg::launch_run_fast(p, rec, agg, vol, s);
+    }
   }
   if (e != cudaSuccess) return fail("tfg_run: kernel launch", e);
   return 0;

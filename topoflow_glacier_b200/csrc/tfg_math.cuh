@@ -12,7 +12,7 @@
 #include <math.h>
 
 #if defined(__CUDACC__)
-#define TFG_HD __host__ __device__ __forceinline__
+#define TFG_HD __device__ __forceinline__
 #else
 #define TFG_HD inline
 #define __constant__ static const
@@ -36,6 +36,18 @@ inline double mk64(int hi, int lo) {
   long long b = ((long long)hi << 32) | (unsigned int)lo; double x; __builtin_memcpy(&x, &b, 8); return x;
 }
 #endif
+
+// Literals of the routines below whose low word is non-zero (such a float64 immediate costs two UMOV / IMAD.MOV
+// per use; from the constant bank it is half an LDCU).  Literals like 1.0, 0.5 or 2^52*1.5 encode in the
+// instruction and stay inline.
+struct MathLit {
+  double exp_scale, exp_nl2h, exp_nl2l, ln2h, ln2l, pio2h, pio2l, pih, pil, tiny, st_u, st_c9, st_c7, st_c5, st_c3,
+      st_d, st_c, st_f;
+};
+__constant__ MathLit kML = {92.332482616893656877, -1.08304246932675596327e-02, -2.98158582698529328128e-12,
+                            6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.5707963267948966,
+                            6.123233995736766e-17, 3.141592653589793, 1.2246467991473532e-16, 1e-290, 0.023101,
+                            1.0 / 9.0, -1.0 / 7.0, 0.2, -1.0 / 3.0, 0.00391838, 1.676331, 4.86035};
 
 template <int N>
 TFG_HD double horner(const double (&c)[N], double x) {
@@ -93,7 +105,7 @@ TFG_HD double div(double a, double b) {
 // sqrt(w) for w >= 0 (w below 1e-290 is treated as 1e-290): MUFU.RSQ64H seed (~2^-20), one Newton step on
 // 1/sqrt (-> 2^-39), Heron correction (-> 2^-77)
 TFG_HD double sqrt_pos(double w) {
-  w = (w > 1e-290) ? w : 1e-290;
+  w = (w > kML.tiny) ? w : kML.tiny;
   double y;
 #if defined(__CUDA_ARCH__)
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
@@ -174,11 +186,11 @@ TFG_HD double div_fast(double a, double b) { return a * rcp3(b); }
 
 // exp(x), |x| < 700
 TFG_HD double exp_tab(double x) {
-  const double t = fma(x, 92.332482616893656877, 6755399441055744.0);  // low word = rint(x * 64/ln2)
+  const double t = fma(x, kML.exp_scale, 6755399441055744.0);  // low word = rint(x * 64/ln2)
   const int k = lo32(t);
   const double fn = t - 6755399441055744.0;
-  double r = fma(fn, -1.08304246932675596327e-02, x);   // -ln2hi/64 (32 significant bits)
-  r = fma(fn, -2.98158582698529328128e-12, r);          // -ln2lo/64
+  double r = fma(fn, kML.exp_nl2h, x);   // -ln2hi/64 (32 significant bits)
+  r = fma(fn, kML.exp_nl2l, r);          // -ln2lo/64
   const double T = TFG_EXPTAB(k & 63);
   const double r2 = r * r;
   const double a = fma(r, TFG_COEF(kExpTQ, 2), TFG_COEF(kExpTQ, 3));
@@ -198,13 +210,13 @@ TFG_HD double log_tab(double x) {
   const double invc = TFG_LOGTAB(i, 0), logc = TFG_LOGTAB(i, 1);
   const double r = fma(z, invc, -1.0);
   const double ed = (double)e;
-  const double w = fma(ed, 6.93147180369123816490e-01, logc);
+  const double w = fma(ed, kML.ln2h, logc);
   const double r2 = r * r;
   const double a0 = fma(r, TFG_COEF(kLogTA, 4), TFG_COEF(kLogTA, 5));
   const double a1 = fma(r, TFG_COEF(kLogTA, 2), TFG_COEF(kLogTA, 3));
   const double a2 = fma(r, TFG_COEF(kLogTA, 0), TFG_COEF(kLogTA, 1));
   const double pa = fma(r2, fma(r2, a2, a1), a0);
-  const double lo = fma(r2, pa, fma(ed, 1.90821492927058770002e-10, r));
+  const double lo = fma(r2, pa, fma(ed, kML.ln2l, r));
   return w + lo;
 }
 
@@ -215,7 +227,7 @@ TFG_HD double asin01(double x) {
   const double s = big ? sqrt_pos(w) : x;
   const double a = fma(s * w, horner_k<2>(kAsinP, w), s);
   // pi/2 = 1.5707963267948966 + 6.123233995736766e-17
-  return big ? (fma(-2.0, a, 1.5707963267948966) + 6.123233995736766e-17) : a;
+  return big ? (fma(-2.0, a, kML.pio2h) + kML.pio2l) : a;
 }
 
 // atan(x), |x| < 1e150
@@ -224,7 +236,7 @@ TFG_HD double atan_core(double x) {
   const bool inv = ax > 1.0;
   const double t = inv ? rcp(ax) : ax;
   const double a0 = t * horner_k<4>(kAtanP, t * t);
-  const double a = inv ? ((1.5707963267948966 - a0) + 6.123233995736766e-17) : a0;
+  const double a = inv ? ((kML.pio2h - a0) + kML.pio2l) : a0;
   return copysign(a, x);
 }
 TFG_HD double atan_f(double x) { return (fabs(x) < 1e150) ? atan_core(x) : atan(x); }
@@ -238,8 +250,8 @@ TFG_HD double atan_diff(double a, double b) {
   const double hi = swap ? ay : ax, lo = swap ? ax : ay;
   const double t = (hi > 0.0) ? lo * rcp3(hi) : 0.0;     // in [0, 1]
   double r = t * horner_k<4>(kAtanP, t * t);
-  r = swap ? ((1.5707963267948966 - r) + 6.123233995736766e-17) : r;
-  r = (x < 0.0) ? ((3.141592653589793 - r) + 1.2246467991473532e-16) : r;
+  r = swap ? ((kML.pio2h - r) + kML.pio2l) : r;
+  r = (x < 0.0) ? ((kML.pih - r) + kML.pil) : r;
   return copysign(r, y);
 }
 
@@ -250,10 +262,10 @@ TFG_HD double atan_diff(double a, double b) {
 // argument (4-term series), and the two middle ones are one atan2.
 TFG_HD double stull_wet_bulb(double T, double RH) {
   const double a1 = horner_k<2>(kStull1, RH);
-  const double u = 0.023101 * RH, u2 = u * u;
-  const double a4 = u * fma(u2, fma(u2, fma(u2, fma(u2, 1.0 / 9.0, -1.0 / 7.0), 0.2), -1.0 / 3.0), 1.0);
-  const double t4 = (0.00391838 * (RH * sqrt_pos(RH))) * a4;
-  return (((T * a1) + atan_diff(T + RH, RH - 1.676331)) + t4) - 4.86035;
+  const double u = kML.st_u * RH, u2 = u * u;
+  const double a4 = u * fma(u2, fma(u2, fma(u2, fma(u2, kML.st_c9, kML.st_c7), kML.st_c5), kML.st_c3), 1.0);
+  const double t4 = (kML.st_d * (RH * sqrt_pos(RH))) * a4;
+  return (((T * a1) + atan_diff(T + RH, RH - kML.st_c)) + t4) - kML.st_f;
 }
 
 // ---- float32 counterparts (coefficients are FFMA immediates; MUFU reciprocal / rsqrt) ------------------------

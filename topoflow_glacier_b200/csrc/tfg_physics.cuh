@@ -13,9 +13,9 @@ namespace tfg {
 // Numeric literals of the physics, kept in __constant__ memory: as immediates every float64 literal costs two
 // UMOV instructions per use; from the constant bank it is one LDCU (often hoisted out of the time loop).
 struct LitTable {
-  double inv_esat0, inv_dew_a, esat10, mag_a, mag_b, esat0, c90, ky_a, ky_b, ky_c, ky_nc, sa_a0, sa_a1, sa_b0, sa_b1, s_a0, s_a1, s_b0, s_b1, dew_c, dew_b, wp_a, wp_b, alb_r1, alb_r0, alb_0, alb_k, alb_ice, alb_bare, st_a, st_b, st_c, st_d, st_e, st_f, kelvin, c12, snow_thr, c3600;
+  double inv_esat0, inv_dew_a, esat10, mag_a, mag_b, esat0, c90, ky_a, ky_b, ky_c, ky_nc, sa_a0, sa_a1, sa_b0, sa_b1, s_a0, s_a1, s_b0, s_b1, dew_c, dew_b, wp_a, wp_b, alb_r1, alb_r0, alb_0, alb_k, alb_ice, alb_bare, st_a, st_b, st_c, st_d, st_e, st_f, kelvin, c12, snow_thr, c3600, c001, c01, pi;
 };
-static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.11, 17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0};
+static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.11, 17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0, 0.01, 0.1, 3.141592653589793};
 #define LIT(field, value) (P::f32 ? Num<P>(value) : Num<P>(static_cast<typename P::raw>(kLit.field)))
 
 // host-precomputed scalars (products/ratios formed in the reference's own order)
@@ -147,7 +147,7 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   } else {
     // th <= -acos(a)/omega  or  th >= acos(a)/omega   <=>   cos(omega*th) <= a   for |omega*th| < pi;
     // outside that range both reference comparisons are true anyway (|T_sr|,|T_ss| <= 12 h).
-    const R pi(3.141592653589793);
+    const R pi = LIT(pi, 3.141592653589793);
     dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (nabs(wt) >= pi) || (nabs(wt + R(s.get(kSDlon))) >= pi);
   }
   if (dark) return R(0.0);                                   // solar_funcs.py:940-941
@@ -227,7 +227,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     rTK = R(fm::rcp3(T_K.v));
     const R inv_p0 = nexp(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)) * R(k.inv_p0c);   // :551-556
     const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));                             // :817
-    e_air = e * 0.01;
+    e_air = e * LIT(c001, 0.01);
     R en(1.0);
     if (!k.satterlund) {
       const R t1a = (LIT(mag_a, 17.3) * T_air) / (T_air + LIT(mag_b, 237.3));                // :788
@@ -245,8 +245,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     dT = T_air - T_surf;
     const R top = R(k.gz) * dT;                                                              // :640-644
     R bot = (uz * uz) * T_K;
-    bot = sel(bot == 0.0, R(0.01), bot);
-    const R L = nlog(nmax((R(k.z) - h_snow) * R(k.inv_z0), R(0.01)));                        // :670
+    bot = sel(bot == 0.0, LIT(c001, 0.01), bot);
+    const R L = nlog(nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)));                        // :670
     const bool stable = top > 0.0;
     const R ten_top = R(10.0) * top;
     const R num = sel(stable, bot, bot - ten_top);
@@ -321,7 +321,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   R em_air;
   if (!k.satterlund) {
     R x;
-    if constexpr (P::lean) x = (e_air * 0.1) * rTK; else x = divk(e_air, 10.0) / T_K;
+    if constexpr (P::lean) x = (e_air * LIT(c01, 0.1)) * rTK; else x = divk(e_air, 10.0) / T_K;
     const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
     em_air = (term1 * R(k.emis_b)) + R(k.canopy);
   } else {
@@ -342,8 +342,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R E_in = Q_sum * dt;
   R SM;
   if constexpr (P::strict) SM = zdiv(zdiv(relu(E_in - Eccs), dt), R(k.rho_lf));
-  else SM = (relu(E_in - Eccs) * R(k.inv_dt)) * R(k.inv_rho_lf);
-  SM = relu(SM);
+  else SM = (relu(E_in - Eccs) * R(k.inv_dt)) * R(k.inv_rho_lf);   // a product of non-negative factors
+  if constexpr (P::strict) SM = relu(SM);
   if constexpr (VOL) s.set(kSVolSM, (R(s.get(kSVolSM)) + (((SM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
@@ -372,12 +372,12 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
   R IM;
   if constexpr (P::strict) IM = relu(zdiv(zdiv(relu(E_in - Ecci), dt), R(k.rho_lf)));
-  else IM = relu((relu(E_in - Ecci) * R(k.inv_dt)) * R(k.inv_rho_lf));
+  else IM = (relu(E_in - Ecci) * R(k.inv_dt)) * R(k.inv_rho_lf);
   IM = sel((h_swe == 0.0) && (previous_swe == 0.0), IM, R(0.0));
   Ecci = relu(Ecci - E_in);
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
-  if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = relu(nmin(IM, h_iwe * R(k.inv_dt)));
+  if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = nmin(IM, h_iwe * R(k.inv_dt));
   if constexpr (VOL) s.set(kSVolIM, (R(s.get(kSVolIM)) + (((IM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
   IM = div3600(nmin(xmul(IM, k3600), h_iwe));

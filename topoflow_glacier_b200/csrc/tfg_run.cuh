@@ -23,10 +23,11 @@ namespace tfg {
 #ifndef TFG_MIN_BLOCKS_F32
 #define TFG_MIN_BLOCKS_F32 8
 #endif
-#ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants live in shared memory, 128 registers suffice
-#define TFG_MIN_BLOCKS_LEAN 4
+#ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants in shared memory, clock rows in the parameter block -> 96 registers
+#define TFG_MIN_BLOCKS_LEAN 5
 #endif
 constexpr int kBlock = TFG_BLOCK;
+constexpr int kMaxLaunchSteps = 128;  // timesteps per launch (longer runs are split by tfg_run); 16.5 KB of parameters
 
 template <class raw>
 struct RunParams {
@@ -40,8 +41,11 @@ struct RunParams {
   raw *h_snow, *h_swe, *h_ice, *h_iwe, *eccs, *ecci, *albedo, *n_days, *SM, *IM, *M_total, *RH;
   raw *vol_P, *vol_PR, *vol_PS, *vol_SM, *vol_IM, *P_max;
   raw* ring;
-  const TimeRow<raw>* rows;  // device, indexed by absolute step
-  const raw* gmt;            // device, [step][n_tz]
+  // Clock-only tables of THIS launch, passed in the kernel parameter block (constant bank): the step index is
+  // warp-uniform, so a row is read with uniform loads straight into the operand slots of the FP64 instructions
+  // instead of occupying 16 vector registers per thread for the whole step.
+  TimeRow<raw> rows[kMaxLaunchSteps];             // indexed by step - step0
+  raw gmt[kMaxLaunchSteps * TFG_MAX_TZ];          // [step - step0][n_tz]
   raw* record;
   uint64_t record_mask;
   int32_t n_rec;
@@ -241,9 +245,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         g4 = ld_stream(fn + 4 * N);
       }
     }
-    const int64_t step = p.step0 + t;
-    const TimeRow<raw> row = p.rows[step];
-    const raw gmt = p.gmt[step * p.n_tz + tz];
+    const TimeRow<raw>& row = p.rows[t];
+    const raw gmt = p.gmt[t * p.n_tz + tz];
     if (!(gmt == gmt_prev)) {  // first step, or DST switch (the offset is piece-wise constant in time)
       gmt_prev = gmt;
       set_zone(gmt);
