@@ -134,8 +134,11 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
     c_u = (cA * R(s.get(kSCB2))) + (sA * R(s.get(kSSB2)));
   }
   // sunrise / sunset arguments, solar_funcs.py:325-326 (horizontal) and :796 (equivalent latitude)
-  const R arg_eq = nmin(nmax(R(-1.0), R(s.get(kSNegTanEq)) * tan_d), R(1.0));
-  const R arg_h = nmin(nmax(R(-1.0), R(s.get(kSNegTanLat)) * tan_d), R(1.0));
+  R arg_eq = R(s.get(kSNegTanEq)) * tan_d, arg_h = R(s.get(kSNegTanLat)) * tan_d;
+  if constexpr (P::strict) {
+    arg_eq = nmin(nmax(R(-1.0), arg_eq), R(1.0));
+    arg_h = nmin(nmax(R(-1.0), arg_h), R(1.0));
+  }  // fast modes compare cosines with the unclamped arguments: beyond +-1 (polar day / night) the outcome is the same
   bool dark;
   if constexpr (P::strict) {
     // T_sr / T_ss exactly as solar_funcs.py:783-830, then the comparison of :939
@@ -208,7 +211,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     P_rain = Pp * R(is_rain ? 1.0 : 0.0);
     P_snow = Pp * R(is_snow ? 1.0 : 0.0);
   } else {
-    P_rain = sel(is_rain, Pp, R(0.0));
+    P_rain = sel(is_snow, R(0.0), Pp);   // sane T_air (no NaN): is_rain == !is_snow
     P_snow = sel(is_snow, Pp, R(0.0));
   }
   if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
@@ -308,8 +311,12 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R tot(window_sum(ring_new.v));                       // :1027-1037
   R n(st.n_days);
   const R thr = LIT(snow_thr, 0.03);
-  n = sel(tot >= thr, R(0.0), n);                           // :1040
-  n = sel(tot < thr, n + R(k.days_per_dt), n);              // :1041
+  if constexpr (P::strict) {
+    n = sel(tot >= thr, R(0.0), n);                         // :1040
+    n = sel(tot < thr, n + R(k.days_per_dt), n);            // :1041
+  } else {
+    n = sel(tot < thr, n + R(k.days_per_dt), R(0.0));       // tot is finite on the sane path
+  }
   R albedo(st.albedo);
   if (h_snow > 0.0) albedo = LIT(alb_0, 0.4) + (LIT(alb_k, 0.44) * nexp((-n) * r));  // :1042-1048
   if (h_snow == 0.0 && h_ice > 0.0) albedo = LIT(alb_ice, 0.3);         // :1049-1053

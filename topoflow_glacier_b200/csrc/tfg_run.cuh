@@ -23,6 +23,9 @@ namespace tfg {
 #ifndef TFG_MIN_BLOCKS_F32
 #define TFG_MIN_BLOCKS_F32 8
 #endif
+#ifndef TFG_CPASYNC  // 1: next-step forcings staged in shared memory by cp.async instead of register prefetches (measured slower)
+#define TFG_CPASYNC 0
+#endif
 #ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants in shared memory, clock rows in the parameter block -> 96 registers
 #define TFG_MIN_BLOCKS_LEAN 5
 #endif
@@ -55,6 +58,16 @@ struct RunParams {
 };
 
 template <class raw> __device__ __forceinline__ raw ld_stream(const raw* p) { return __ldcs(p); }
+
+// One element global -> shared without a register in between (LDGSTS): the next step's forcings are in flight for a
+// whole timestep, and as register prefetches they would pin ten registers for that long.
+template <class raw> __device__ __forceinline__ void cp_async_elem(raw* dst_smem, const raw* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "n"((int)sizeof(raw))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---- TMA bulk-copy staging of forcing tiles (cp.async.bulk + mbarrier, SASS: UBLKCP / SYNCS) -----------------
 // A block of kBlock cells needs, per timestep, five contiguous rows of kBlock elements (one per forcing).  One
@@ -179,6 +192,16 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   __shared__ alignas(128) raw sm_force[TMA ? kStages : 1][TFG_N_FORCING][TMA ? kBlock : 1];
   __shared__ uint64_t bar_full[kStages], bar_empty[kStages];
   const raw* fblock = p.forcing + (int64_t)blockIdx.x * kBlock;  // first cell of this block, step 0, variable 0
+  // default path: every thread copies its own five forcings of step t+1 into its column of a two-deep
+  // shared-memory stage while step t is computed (no cross-thread traffic, hence no barrier)
+  constexpr bool kCp = TFG_CPASYNC && !TMA;
+  __shared__ raw sm_next[kCp ? 2 : 1][TFG_N_FORCING][kCp ? kBlock : 1];
+  auto stage_forcing = [&](int step_t) {
+    const raw* fn = f + (int64_t)step_t * (TFG_N_FORCING * N);
+#pragma unroll
+    for (int v = 0; v < TFG_N_FORCING; ++v) cp_async_elem(&sm_next[step_t & 1][v][threadIdx.x], fn + (int64_t)v * N);
+    cp_async_commit();
+  };
   auto issue_stage = [&](int step_t) {  // elected thread: five row copies for timestep step_t
     const int sg = step_t % kStages;
     mbar_expect_tx(&bar_full[sg], (unsigned)(TFG_N_FORCING * kBlock * sizeof(raw)));
@@ -195,6 +218,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     __syncthreads();
     if (threadIdx.x == 0)
       for (int i = 0; i < kStages && i < p.n_steps; ++i) issue_stage(i);
+  } else if constexpr (kCp) {
+    stage_forcing(0);
   } else {
     f0 = ld_stream(f); f1 = ld_stream(f + N); f2 = ld_stream(f + 2 * N); f3 = ld_stream(f + 3 * N);
     f4 = ld_stream(f + 4 * N);
@@ -237,13 +262,18 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         mbar_wait(&bar_empty[(t - 1) % kStages], (unsigned)(((t - 1) / kStages) & 1));
         issue_stage(t - 1 + kStages);
       }
-    } else {
+    } else if constexpr (!kCp) {
       g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
       if (t + 1 < p.n_steps) {  // prefetch the next step's forcings
         const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
         g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
         g4 = ld_stream(fn + 4 * N);
       }
+    } else {
+      cp_async_wait_all();  // this thread's copies of step t have landed
+      f0 = sm_next[t & 1][0][threadIdx.x]; f1 = sm_next[t & 1][1][threadIdx.x]; f2 = sm_next[t & 1][2][threadIdx.x];
+      f3 = sm_next[t & 1][3][threadIdx.x]; f4 = sm_next[t & 1][4][threadIdx.x];
+      if (t + 1 < p.n_steps) stage_forcing(t + 1);
     }
     const TimeRow<raw>& row = p.rows[t];
     const raw gmt = p.gmt[t * p.n_tz + tz];
@@ -351,7 +381,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         }
       }
     }
-    if constexpr (!TMA) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
+    if constexpr (!TMA && !kCp) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
     r_old = r_next;
     slot = slot_next;
   }
