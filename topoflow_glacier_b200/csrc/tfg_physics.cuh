@@ -193,11 +193,13 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
 
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
-template <class P, bool VOL, class Cell, class WindowFn>
+// `mid_step()` is called once the pressure / humidity / wind forcings are dead (after the turbulent fluxes): the
+// kernel issues the next step's forcing loads there, so that they do not hold registers through the met block.
+template <class P, bool VOL, class Cell, class WindowFn, class MidFn>
 __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
                                           Cell& s, Num<P> LC, CellState<typename P::raw>& st,
                                           Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
-                                          WindowFn&& window_sum, StepOut<typename P::raw>& o) {
+                                          WindowFn&& window_sum, MidFn&& mid_step, StepOut<typename P::raw>& o) {
   using R = Num<P>;
   const R dt(k.dt);
   R h_snow(st.h_snow), h_swe(st.h_swe), h_ice(st.h_ice), h_iwe(st.h_iwe), Eccs(st.eccs), Ecci(st.ecci);
@@ -302,6 +304,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     e_surf = RH * e_sat_surf;
     Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
   }
+  mid_step();
   // ---- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471
   const R solar_noon = (LIT(c12, 12.0) + LC) + R(tr.TE);
   const R th = R(tr.clock_hour) - solar_noon;

@@ -224,7 +224,11 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     f0 = ld_stream(f); f1 = ld_stream(f + N); f2 = ld_stream(f + 2 * N); f3 = ld_stream(f + 3 * N);
     f4 = ld_stream(f + 4 * N);
   }
-  raw r_old = ring[(int64_t)slot * N];
+  // float32 kernel: the slot pointer walks through the window (no 64-bit multiply per step); the float64 kernels
+  // are register-bound and recompute the address instead of carrying two more pointers
+  constexpr bool kWalk = P::f32;
+  raw* ring_cur = ring + (int64_t)slot * N;
+  raw r_old = *ring_cur;
   R LC(0.0);
   auto set_zone = [&](raw gmt) {
     if constexpr (P::strict) {
@@ -263,12 +267,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         issue_stage(t - 1 + kStages);
       }
     } else if constexpr (!kCp) {
-      g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
-      if (t + 1 < p.n_steps) {  // prefetch the next step's forcings
-        const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
-        g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
-        g4 = ld_stream(fn + 4 * N);
-      }
+      // the next step's forcings are requested from inside the step (prefetch below)
     } else {
       cp_async_wait_all();  // this thread's copies of step t have landed
       f0 = sm_next[t & 1][0][threadIdx.x]; f1 = sm_next[t & 1][1][threadIdx.x]; f2 = sm_next[t & 1][2][threadIdx.x];
@@ -281,25 +280,46 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       gmt_prev = gmt;
       set_zone(gmt);
     }
-    const int slot_next = (slot + 1 == slots) ? 0 : slot + 1;
+    const bool wrap = (slot + 1 == slots);
+    const int slot_next = wrap ? 0 : slot + 1;
+    raw* ring_next = kWalk ? (wrap ? ring : ring_cur + N) : ring + (int64_t)slot_next * N;
     raw r_next = 0;
     R tot_now;
     auto window = [&](raw ring_new_raw) -> raw {
       const R ring_new(ring_new_raw);
-      if (active) ring[(int64_t)slot * N] = ring_new.v;  // np.roll(-1) + write of the newest slot, :1027-1033
+      if (active) *(kWalk ? ring_cur : ring + (int64_t)slot * N) = ring_new.v;  // np.roll(-1) + write of the newest slot, :1027-1033
       if (exact) {
         tot_now = window_sum_exact<P>(ring, N, slots, slot);
       } else {
         tot = xadd(xsub(tot, R(r_old)), ring_new);
-        tot_hi = nmax(tot_hi, nabs(tot));
-        if (nabs(tot - 0.03) <= guard * nmax(tot_hi, R(1.0))) {
+        bool near_threshold;
+        if constexpr (P::lean) {
+          // the incremental sum drifts by < 330 roundings of the largest sum seen during a launch (72 seed
+          // additions + 2 per step, <= 128 steps): below 1e4 m that is < 4e-10 m, so a fixed band around the
+          // threshold suffices; larger sums (absurd forcing) take the exact path every step
+          near_threshold = (nabs(tot - LIT(snow_thr, 0.03)) <= 1e-9) || (__double2hiint(tot.v) >= 0x40c38800);
+        } else {
+          tot_hi = nmax(tot_hi, nabs(tot));
+          near_threshold = nabs(tot - 0.03) <= guard * nmax(tot_hi, R(1.0));
+        }
+        if (near_threshold) {
           tot = window_sum_exact<P>(ring, N, slots, slot);
           tot_hi = nabs(tot);
         }
         tot_now = tot;
       }
-      r_next = ring[(int64_t)slot_next * N];  // next step's oldest entry (after this step's store)
+      r_next = *ring_next;  // next step's oldest entry (after this step's store)
       return tot_now.v;
+    };
+    auto prefetch = [&]() {  // next step's forcings, issued mid-step (see cell_step)
+      if constexpr (!TMA && !kCp) {
+        g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
+        if (t + 1 < p.n_steps) {
+          const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
+          g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
+          g4 = ld_stream(fn + 4 * N);
+        }
+      }
     };
     if constexpr (P::lean) {
       // The lean math cores assume physically sane arguments.  Bit tests on the high words (no FP64 pipe):
@@ -313,18 +333,18 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
                         in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
                         (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
       if (__all_sync(0xffffffffu, sane && state_ok)) {
-        cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+        cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
       } else {
         // Same step in the strict arithmetic (libdevice, IEEE division, NumPy's NaN rules): whatever the input
         // -- missing data, absurd values -- the cell behaves like the reference, NaN poisoning included.
         using S = Num<StrictF64>;
         const S LCs = ((S(gmt_prev) * 15.0) - S(lon.v)) / 15.0;
-        cell_step<StrictF64, VOL>(p.k, row, s, LCs, st, S(f0), S(f1), S(f2), S(f3), S(f4), window, o);
+        cell_step<StrictF64, VOL>(p.k, row, s, LCs, st, S(f0), S(f1), S(f2), S(f3), S(f4), window, prefetch, o);
         state_ok = finite(st.h_snow) && finite(st.h_swe) && finite(st.h_ice) && finite(st.h_iwe) &&
                    finite(st.eccs) && finite(st.ecci) && finite(st.albedo) && finite(st.n_days);
       }
     } else {
-      cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, o);
+      cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
     }
 
     if constexpr (REC) {
@@ -384,6 +404,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     if constexpr (!TMA && !kCp) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
     r_old = r_next;
     slot = slot_next;
+    if constexpr (kWalk) ring_cur = ring_next;
   }
 
   if (active) {
