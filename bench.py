@@ -239,7 +239,9 @@ def run_gpu_arm(args):
     elev = raw_attrs["elev"].to(eng.dtype)
     forcing = torch.empty(Tc, 5, n_cells, dtype=eng.dtype, device=dev)
     eng.synth_forcing(forcing, 0, Tc, elev, seed=20121001 + rank)
-    agg = BasinAggregates(Tc, N_BASIN, device=dev)
+    # --agg exact: order-independent fixed-point accumulators + integer all-reduce (bit-identical for any N)
+    agg_exps = eng.agg_exponents() if args.agg == "exact" else None
+    agg = BasinAggregates(Tc, N_BASIN, device=dev, exponents=agg_exps)
     fp64_peak = eng.measure_fp64_peak()  # DFMA microbenchmark, before the timed region
     torch.cuda.synchronize()
 
@@ -263,8 +265,7 @@ def run_gpu_arm(args):
         chk.close()
 
     def one_step():
-        agg.zero()
-        eng.run(forcing, Tc, basin_agg=agg.buffer)
+        eng.run(forcing, Tc, basin_agg=agg.zero())
         agg.reduce()
 
     for _ in range(args.warmup):
@@ -281,10 +282,10 @@ def run_gpu_arm(args):
     start_all, end_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start_all.record()
     for _ in range(args.steps):
-        agg.zero()
+        tgt = agg.zero()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.run(forcing, Tc, basin_agg=agg.buffer)
+        eng.run(forcing, Tc, basin_agg=tgt)
         b.record()
         agg.reduce()
         evs.append((a, b))
@@ -313,10 +314,10 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         ev2 = []
         for _ in range(max(2, args.steps // 2)):
-            agg.zero()
+            tgt = agg.zero()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            eng.run(forcing, Tc, basin_agg=agg.buffer)
+            eng.run(forcing, Tc, basin_agg=tgt)
             b.record()
             ev2.append((a, b))
         torch.cuda.synchronize()
@@ -336,7 +337,7 @@ def run_gpu_arm(args):
     del raw_dev, blk
     streamer = ForcingStreamer(eng, Te, raw_dtype=args.e2e_raw)
     out_host = [torch.empty(8, n_cells, dtype=eng.dtype).pin_memory() for _ in range(2)]
-    agg_e = [BasinAggregates(Te, N_BASIN, device=dev) for _ in range(2)]
+    agg_e = [BasinAggregates(Te, N_BASIN, device=dev, exponents=agg_exps) for _ in range(2)]
     agg_host = [torch.empty(Te, N_BASIN, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
     out_rows = torch.tensor([0, 1, 8, 2, 3, 9, 10, 11], device=dev)  # h_snow,h_swe,SM,h_ice,h_iwe,IM,M_total,RH
     drain = torch.cuda.Stream(device=dev)
@@ -349,8 +350,7 @@ def run_gpu_arm(args):
         for i, chunk in enumerate(streamer.chunks([raw_host] * k_steps)):
             j = i % 2
             cur.wait_event(drained[j])  # result buffers of two blocks ago have left the device
-            agg_e[j].zero()
-            eng.run(chunk, chunk.shape[0], basin_agg=agg_e[j].buffer)
+            eng.run(chunk, chunk.shape[0], basin_agg=agg_e[j].zero())
             agg_e[j].reduce()
             snap = eng.state.index_select(0, out_rows)
             done = torch.cuda.Event()
@@ -412,7 +412,7 @@ def run_gpu_arm(args):
             "dtype": "f32" if mode == "f32" else "f64", "data": "synthetic",
             "config": {"workload": "synthetic 4096x4096 glacierised raster per GPU (BASELINE configs[3]), hourly forcing",
                        "cells_per_gpu": n_cells, "timesteps_per_step": Tc, "arithmetic_mode": mode,
-                       "basin_aggregates": N_BASIN, "forcing": "device-resident chunk, Philox synthetic, reused each step",
+                       "basin_aggregates": N_BASIN, "aggregate_sums": args.agg, "forcing": "device-resident chunk, Philox synthetic, reused each step",
                        "l2": f"inputs {es * 5 * cell_steps / 1e9:.1f} GB per launch >> 126 MB L2 (no flush needed)",
                        "parallelism": f"cells sharded x{world}, all_reduce of basin aggregates"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -449,6 +449,8 @@ def main():
     ap.add_argument("--e2e-raw", default="float32", choices=["float32", "float64"])
     ap.add_argument("--cpu-cells", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=24)
+    ap.add_argument("--agg", default="float", choices=["float", "exact"],
+                    help="basin sums: float64 atomics, or order-independent fixed-point accumulators (TFG_OPT_EXACT_AGG)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-coherent", action="store_true")
     args = ap.parse_args()

@@ -128,6 +128,15 @@ TFG_API int tfg_mode(const tfg_ctx* ctx);
 /* tuning switches; TFG_OPT_TMA_STAGING: forcing tiles reach shared memory through cp.async.bulk + mbarrier
  * (4 stages) instead of per-thread prefetching loads; results are bit-identical either way */
 #define TFG_OPT_TMA_STAGING 1
+/* TFG_OPT_EXACT_AGG: order-independent basin aggregates.  value = 0 switches it off; otherwise
+ * value = 1<<24 | (E2+128)<<16 | (E1+128)<<8 | (E0+128), E_q the binary exponent that bounds a 32-cell partial sum
+ * of aggregate q (|partial| < 2^E_q).  tfg_run then reads `basin_agg` as int64 [n_steps][n_basin][TFG_N_AGG][2]
+ * followed by ONE trailing int64 counter: every contribution is split into two fixed-point words
+ * (value = hi * 2^(E_q-40) + lo * 2^(E_q-82)) that are added with integer atomics, so the sums do not depend on the
+ * order of the atomics, on the launch geometry or on how cells are sharded over GPUs (32-cell aligned shards), and
+ * an integer all-reduce of the accumulators is exact.  Contributions that are not finite or exceed 2^E_q are left
+ * out and counted in the trailing word.                                                                        */
+#define TFG_OPT_EXACT_AGG 2
 TFG_API int tfg_set_option(tfg_ctx* ctx, int option, int64_t value);
 TFG_API size_t tfg_elem_size(const tfg_ctx* ctx);
 
@@ -135,8 +144,9 @@ TFG_API size_t tfg_elem_size(const tfg_ctx* ctx);
 TFG_API int tfg_set_constants(tfg_ctx* ctx, const tfg_constants* c);
 TFG_API int tfg_bind_static(tfg_ctx* ctx, int64_t n_cells, const tfg_statics* s);
 TFG_API int tfg_bind_state(tfg_ctx* ctx, const tfg_state* s);
-/* host tables for steps [0, n_steps): rows[n_steps], gmt_offset_hours[n_steps][n_tz]; copied to the
- * device (replaces solar.gmt_offset_hours, solar_funcs.py:1616-1637, evaluated on the host)      */
+/* host tables for steps [0, n_steps): rows[n_steps], gmt_offset_hours[n_steps][n_tz]; copied by the library
+ * (each launch carries its <= 128 rows in the kernel parameter block); replaces solar.gmt_offset_hours,
+ * solar_funcs.py:1616-1637, evaluated on the host                                                 */
 TFG_API int tfg_bind_time(tfg_ctx* ctx, const tfg_time_row* rows, const double* gmt_offset_hours, int64_t n_steps,
                   int n_tz, void* stream);
 
@@ -147,12 +157,12 @@ TFG_API int tfg_bind_time(tfg_ctx* ctx, const tfg_time_row* rows, const double* 
  *   forcing      dev [n_steps][5][n_cells] (TFG_N_FORCING order)
  *   record       dev [n_steps][popcount(record_mask)][n_cells] or NULL: per-step series of the
  *                quantities whose tfg_rec bit is set, rows in ascending bit order
- *   basin_agg    dev [n_steps][n_basin][TFG_N_AGG] or NULL: ACCUMULATED INTO (zero it first);
- *                always float64; replaces np.sum(...) at :567-568,:1486-1494 and the driver-side
- *                `* da_m2` (examples/run_topoflow_glacier.py:115)
+ *   basin_agg    dev [n_steps][n_basin][TFG_N_AGG] float64 or NULL: ACCUMULATED INTO (zero it first);
+ *                replaces np.sum(...) at :567-568,:1486-1494 and the driver-side `* da_m2`
+ *                (examples/run_topoflow_glacier.py:115); int64 fixed-point accumulators under TFG_OPT_EXACT_AGG
  * n_steps == 1 re-sums the snowfall window exactly every step (the literal update()).          */
 TFG_API int tfg_run(tfg_ctx* ctx, const void* forcing, int64_t step0, int32_t n_steps, void* record, uint64_t record_mask,
-            double* basin_agg, int32_t n_basin, void* stream);
+            void* basin_agg, int32_t n_basin, void* stream);
 
 /* ---- forcing ingestion (replaces the driver loop, examples/run_topoflow_glacier.py:40-73) ---- */
 /* cudaMemcpyAsync of one pinned host block to the device on `stream`, then records `done_event`

@@ -22,7 +22,10 @@ eng = MeltEngine(None, default_constants(), "2012100100", zones=[-8.0], mode=a.m
 f = torch.empty(a.steps, 5, a.cells, dtype=eng.dtype, device=dev)
 eng.step_index = 2400  # start in January: snow everywhere, mixed day/night
 eng.synth_forcing(f, 2400, a.steps, raw["elev"].to(eng.dtype), 7, a.storm)
-agg = torch.zeros(a.steps, 4096, 3, dtype=torch.float64, device=dev) if a.agg else None
+agg = torch.zeros(a.steps, 4096, 3, dtype=torch.float64, device=dev) if a.agg == 1 else None
+if a.agg == 2:  # order-independent fixed-point accumulators (TFG_OPT_EXACT_AGG)
+    from topoflow_glacier_b200.sharding import BasinAggregates
+    agg = BasinAggregates(a.steps, 4096, device=dev, exponents=eng.agg_exponents()).accumulator
 torch.cuda.synchronize()
 for i in range(a.launches):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -196,6 +196,53 @@ def test_basin_aggregates_match_host_sums(cuda_device):
         eng.close()
 
 
+def test_exact_basin_aggregates_are_order_and_sharding_independent(cuda_device):
+    """TFG_OPT_EXACT_AGG: fixed-point integer accumulators.  The sums equal the host sums, repeat bit for bit, and
+    one engine over all cells == two engines over 128-aligned shards whose integer words are added (what the
+    int64 all-reduce does on N GPUs), bit for bit; the float path only agrees to rounding."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.sharding import BasinAggregates, basin_sums_host, shard_bounds
+
+    N, T, NB = 6000, 10, 23
+    statics, forcing = bench.synthetic_host_sample(N, T, seed=11)
+    rng = np.random.default_rng(2)
+    basin_id = rng.integers(0, NB, N).astype(np.int32)      # warps straddle basins: per-lane atomics
+    basin_id[1024:4096] = np.sort(basin_id[1024:4096])      # ... and long uniform runs: warp butterflies
+    f = torch.as_tensor(forcing).cuda()
+
+    def run(lo, hi, exps=None):
+        st = {k: v[lo:hi] for k, v in statics.items()}
+        eng = MeltEngine(st, default_constants(), "2013040100", zones=[-8.0], mode="f64_fast", basin_id=basin_id[lo:hi],
+                         n_basin=NB, horizon_steps=T + 1)
+        agg = BasinAggregates(T, NB, device=cuda_device, exponents=exps or eng.agg_exponents())
+        rec = eng.run(f[:, :, lo:hi].contiguous(), record=("M_total", "h_swe", "h_iwe"), basin_agg=agg.zero())
+        torch.cuda.synchronize()
+        out = (agg, {k: v.cpu().numpy() for k, v in rec.items()}, eng.agg_exponents())
+        eng.close()
+        return out
+
+    whole, rec, exps = run(0, N)
+    assert whole.n_left_out == 0
+    again, _, _ = run(0, N)
+    assert torch.equal(whole.accumulator, again.accumulator)           # independent of the order of the atomics
+    acc = torch.zeros_like(whole.accumulator)
+    for r in range(2):
+        lo, hi = shard_bounds(N, 2, r)
+        part, _, _ = run(lo, hi, exps)                                  # same exponents on every shard
+        acc += part.accumulator
+    assert torch.equal(acc, whole.accumulator)                         # sharding-independent, bit for bit
+    got = whole.reduce() or whole.buffer.cpu().numpy()
+    da_m2 = statics["da"] * 1e6
+    for t in range(T):
+        for j, k in enumerate(("M_total", "h_swe", "h_iwe")):
+            want = basin_sums_host(rec[k][t], da_m2, basin_id, NB)
+            np.testing.assert_allclose(got[t, :, j], want, rtol=1e-13, atol=1e-20)
+
+
 def test_checkpoint_resume_is_bit_identical(tmp_path, cuda_device):
     """state + snowfall window + step counter saved mid-run, resumed in a fresh model == uninterrupted run."""
     import torch

@@ -162,6 +162,15 @@ for t in range(T):
     for j in range(3):
         agg.buffer[t, :, j] = torch.as_tensor(basin_sums_host(vals[t, j, lo:hi], da[lo:hi], basin[lo:hi], NB))
 agg.reduce()
+# exact mode: the int64 words are all-reduced (exactly) and decoded; value = hi * 2^(E-40) + lo * 2^(E-82)
+ex = BasinAggregates(T, NB, exponents=(3, 20, 20))
+words = torch.as_tensor(rng.integers(-2**40, 2**40, (2, T * NB * 3 * 2 + 1)))  # same draw on both ranks
+ex.accumulator.copy_(words[rank])
+ex.reduce()
+tot = (words[0] + words[1])[:-1].view(T, NB, 3, 2).double()
+e = torch.tensor([3.0, 20.0, 20.0], dtype=torch.float64)
+assert torch.equal(ex.buffer, tot[..., 0] * torch.exp2(e - 40) + tot[..., 1] * torch.exp2(e - 82))
+assert ex.n_left_out == int(words[0, -1] + words[1, -1])
 area = agg.basin_area(torch.as_tensor(da[lo:hi]), torch.as_tensor(basin[lo:hi]))
 for t in range(T):
     for j in range(3):

@@ -12,6 +12,7 @@ F64_STRICT, F64_FAST, F32 = 0, 1, 2
 MODE_NAMES = {"f64": F64_STRICT, "f64_strict": F64_STRICT, "strict": F64_STRICT, "f64_fast": F64_FAST,
               "fast": F64_FAST, "f32": F32, "fp32": F32, "fp64": F64_STRICT}
 OPT_TMA_STAGING = 1
+OPT_EXACT_AGG = 2
 N_FORCING = 5
 N_AGG = 3
 MAX_TZ = 8

@@ -45,6 +45,7 @@ struct tfg_ctx {
   int64_t n_time = 0;
   int n_tz = 1;
   int use_tma = 0;  // forcing tiles staged by the TMA copy engine (tfg_set_option)
+  int64_t exact_agg = 0;  // TFG_OPT_EXACT_AGG value (0 = floating-point atomics)
 };
 
 namespace {
@@ -103,7 +104,7 @@ tfg::Consts<raw> derive(const tfg_constants& c) {
 
 template <class raw>
 tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, void* record,
-                                uint64_t mask, double* agg, int32_t n_basin) {
+                                uint64_t mask, void* agg, int32_t n_basin, long long* agg_bad) {
   tfg::RunParams<raw> p{};
   p.n_cells = x->n_cells;
   p.step0 = step0;
@@ -135,6 +136,10 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
   p.record_mask = mask;
   p.n_rec = __builtin_popcountll(mask);
   p.basin_agg = agg;
+  p.agg_exact = x->exact_agg != 0;
+  p.agg_bad = agg_bad;
+  for (int q = 0; q < TFG_N_AGG; ++q)  // 2^(40 - E_q): scales a partial sum into the hi fixed-point word
+    p.agg_up[q] = ldexp(1.0, 40 - ((int)((x->exact_agg >> (8 * q)) & 0xff) - 128));
   p.n_basin = n_basin;
   p.k = derive<raw>(x->c);
   return p;
@@ -280,6 +285,7 @@ size_t tfg_elem_size(const tfg_ctx* x) { return (x && x->mode == TFG_F32) ? 4 : 
 int tfg_set_option(tfg_ctx* x, int option, int64_t value) {
   if (!x) return fail("tfg_set_option: NULL context");
   if (option == TFG_OPT_TMA_STAGING) { x->use_tma = value != 0; return 0; }
+  if (option == TFG_OPT_EXACT_AGG) { x->exact_agg = value; return 0; }
   return fail("tfg_set_option: unknown option");
 }
 
@@ -332,7 +338,7 @@ int tfg_bind_time(tfg_ctx* x, const tfg_time_row* rows, const double* gmt, int64
 }
 
 int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, void* record, uint64_t record_mask,
-            double* basin_agg, int32_t n_basin, void* stream) {
+            void* basin_agg, int32_t n_basin, void* stream) {
   if (!x || !forcing) return fail("tfg_run: NULL argument");
   if (!x->have_consts || !x->have_static || !x->have_state || x->h_rows.empty())
     return fail("tfg_run: constants, statics, state and time tables must be bound first");
@@ -351,11 +357,13 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
     const int32_t nt = std::min<int32_t>(tfg::kMaxLaunchSteps, n_steps - t0);
     const void* f = static_cast<const char*>(forcing) + (size_t)t0 * TFG_N_FORCING * x->n_cells * es;
     void* r = record ? static_cast<char*>(record) + (size_t)t0 * __builtin_popcountll(record_mask) * x->n_cells * es : nullptr;
-    double* a = basin_agg ? basin_agg + (size_t)t0 * n_basin * TFG_N_AGG : nullptr;
+    // float64 sums: 8 B per entry; exact mode: two int64 words per entry (the trailing counter stays at the end)
+    void* a = basin_agg ? static_cast<char*>(basin_agg) + (size_t)t0 * n_basin * TFG_N_AGG * (x->exact_agg ? 16 : 8) : nullptr;
+    long long* agg_bad = (basin_agg && x->exact_agg) ? static_cast<long long*>(basin_agg) + (size_t)n_steps * n_basin * TFG_N_AGG * 2 : nullptr;
     if (x->mode == TFG_F32) {
-      e = tfg::launch_run_f32(make_params<float>(x, f, step0 + t0, nt, r, record_mask, a, n_basin), rec, agg, vol, s);
+      e = tfg::launch_run_f32(make_params<float>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad), rec, agg, vol, s);
     } else {
-      auto p = make_params<double>(x, f, step0 + t0, nt, r, record_mask, a, n_basin);
+      auto p = make_params<double>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad);
       e = (x->mode == TFG_F64_STRICT) ? tfg::launch_run_strict(p, rec, agg, vol, s) : tfg::launch_run_fast(p, rec, agg, vol, s);
     }
   }

@@ -52,8 +52,10 @@ struct RunParams {
   raw* record;
   uint64_t record_mask;
   int32_t n_rec;
-  double* basin_agg;
-  int32_t n_basin;
+  void* basin_agg;      // float64 sums, or int64 {hi, lo} fixed-point accumulators when agg_exact
+  int32_t n_basin, agg_exact;
+  double agg_up[TFG_N_AGG];  // 2^(40 - E_q)
+  long long* agg_bad;   // exact mode: count of contributions left out (non-finite or >= 2^E_q)
   Consts<raw> k;
 };
 
@@ -128,6 +130,20 @@ __device__ __noinline__ Num<P> window_sum_exact(const typename P::raw* ring, int
   R res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
   for (; i < slots; ++i) res = res + next();
   return res;
+}
+
+// One contribution to an exact basin aggregate: v * up = a + r with a = trunc (|a| < 2^40), b = trunc(r * 2^42);
+// both words are added with integer atomics (associative, hence order-independent).
+__device__ __forceinline__ void agg_add_exact(long long* acc, double v, double up, long long* bad) {
+  const double s = v * up;  // a power-of-two scaling: exact
+  if (!(fabs(s) < 1099511627776.0)) {  // also catches NaN
+    if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(bad), 1ull);
+    return;
+  }
+  const long long a = __double2ll_rz(s);
+  const long long b = __double2ll_rz((s - (double)a) * 4398046511104.0);
+  if (a) atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)a);
+  if (b) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + 1, (unsigned long long)b);
 }
 
 template <class P, bool REC, bool AGG, bool VOL, bool TMA = false>
@@ -379,7 +395,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         double v0 = active ? (double)o.M_total * da : 0.0;
         double v1 = active ? (double)st.h_swe * da : 0.0;
         double v2 = active ? (double)st.h_iwe * da : 0.0;
-        double* dst = p.basin_agg + ((int64_t)t * p.n_basin + basin) * TFG_N_AGG;
+        const int64_t entry = ((int64_t)t * p.n_basin + basin) * TFG_N_AGG;
+        double* dst = static_cast<double*>(p.basin_agg) + entry;
+        long long* acc = static_cast<long long*>(p.basin_agg) + 2 * entry;
         if (warp_uniform) {
           // three sums in one butterfly: after the first two exchanges every lane is responsible for ONE of the
           // quantities (lanes 0-7: v0, 8-15: v1, 16-23: v2), so 12 shuffles instead of 30
@@ -395,9 +413,17 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
           k += __shfl_xor_sync(full, k, 4);
           k += __shfl_xor_sync(full, k, 2);
           k += __shfl_xor_sync(full, k, 1);
-          if ((lane & 7) == 0 && lane < 24) atomicAdd(dst + (lane >> 3), k);
+          if ((lane & 7) == 0 && lane < 24) {
+            if (p.agg_exact) agg_add_exact(acc + 2 * (lane >> 3), k, p.agg_up[lane >> 3], p.agg_bad);
+            else atomicAdd(dst + (lane >> 3), k);
+          }
         } else if (active) {
-          atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2);
+          if (p.agg_exact) {
+            agg_add_exact(acc + 0, v0, p.agg_up[0], p.agg_bad); agg_add_exact(acc + 2, v1, p.agg_up[1], p.agg_bad);
+            agg_add_exact(acc + 4, v2, p.agg_up[2], p.agg_bad);
+          } else {
+            atomicAdd(dst + 0, v0); atomicAdd(dst + 1, v1); atomicAdd(dst + 2, v2);
+          }
         }
       }
     }

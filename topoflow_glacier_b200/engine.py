@@ -74,6 +74,7 @@ class MeltEngine:
             raise ValueError("dt must give between 1 and 72 snowfall-window slots")
         self.step_index = 0
         self.n_basin = int(n_basin)
+        self._exact_agg, self._agg_exp = 0, None
 
         with torch.cuda.device(self.device):
             ctx = C.c_void_p()
@@ -211,8 +212,16 @@ class MeltEngine:
         if basin_agg is not None:
             if self.basin_id is None or self.n_basin <= 0:
                 raise RuntimeError("basin aggregates requested but the engine was built without basin_id / n_basin")
-            if basin_agg.dtype != torch.float64 or basin_agg.numel() < T * self.n_basin * _lib.N_AGG:
+            exact = 0
+            if basin_agg.dtype == torch.int64:  # order-independent fixed-point accumulators (sharding.BasinAggregates)
+                if basin_agg.numel() < T * self.n_basin * _lib.N_AGG * 2 + 1:
+                    raise ValueError("exact basin_agg must be int64 [n_steps * n_basin * 3 * 2 + 1]")
+                exact = self.exact_agg_option()
+            elif basin_agg.dtype != torch.float64 or basin_agg.numel() < T * self.n_basin * _lib.N_AGG:
                 raise ValueError("basin_agg must be float64 [n_steps, n_basin, 3]")
+            if exact != self._exact_agg:
+                _lib.check(self.lib.tfg_set_option(self.ctx, _lib.OPT_EXACT_AGG, exact), "tfg_set_option")
+                self._exact_agg = exact
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tfg_run(
                 self.ctx, forcing.data_ptr(), self.step_index, T, rec_t.data_ptr() if rec_t is not None else None,
@@ -220,6 +229,22 @@ class MeltEngine:
                 "tfg_run")
         self.step_index += T
         return {k: rec_t[:, i] for i, k in enumerate(names)} if rec_t is not None else {}
+
+    # ---- order-independent basin aggregates (TFG_OPT_EXACT_AGG, include/tfglacier.h) ---------------------------
+    def agg_exponents(self):
+        """Binary exponents E_q with |32-cell partial of aggregate q| < 2^E_q for physically possible values:
+        M_total < 2^-8 m/s (10 m/h of rain is 2.8e-3), water-equivalent depths < 2^17 m."""
+        if self._agg_exp is None:
+            da_max = float(self.static["da_m2"].max().item())
+            e_da = int(np.ceil(np.log2(max(da_max, 1e-30) * 32.0)))
+            self._agg_exp = (e_da - 8, e_da + 17, e_da + 17)
+        return self._agg_exp
+
+    def exact_agg_option(self) -> int:
+        e = self.agg_exponents()
+        if not all(-128 <= x < 128 for x in e):
+            raise ValueError("cell areas out of range for exact aggregates")
+        return (1 << 24) | ((e[2] + 128) << 16) | ((e[1] + 128) << 8) | (e[0] + 128)
 
     def step(self, record: Optional[Iterable[str]] = None):
         """One literal ``update()`` from the current input block."""

@@ -60,26 +60,66 @@ def basin_sums_host(values: np.ndarray, da_m2: np.ndarray, basin_id: np.ndarray,
 class BasinAggregates:
     """Per-rank partial sums -> global sums.
 
-    ``buffer`` is the ``[T_chunk, n_basin, 3]`` float64 tensor the kernel accumulates into; ``reduce`` makes it
-    global (in place).  Works on CUDA tensors with NCCL and on CPU tensors with gloo.
+    Default: ``buffer`` is the ``[T_chunk, n_basin, 3]`` float64 tensor the kernel accumulates into with
+    floating-point atomics; ``reduce`` makes it global (in place) with one ``all_reduce(SUM)``.  Reproducible to
+    rounding (~1e-15), not bit for bit: the order of the atomics is not fixed.
+
+    ``exponents=(E0, E1, E2)`` (``MeltEngine.agg_exponents()``) selects ORDER-INDEPENDENT sums instead: the kernel
+    splits every contribution into two fixed-point int64 words and adds them with integer atomics
+    (``TFG_OPT_EXACT_AGG``); ``accumulator`` is that int64 tensor (pass it to ``MeltEngine.run(basin_agg=...)``),
+    ``reduce`` all-reduces the integers -- exactly -- and decodes them into ``buffer``.  The result is bit-identical
+    for any GPU count (shards are 128-cell aligned), launch split or scheduling order.  Works on CUDA tensors with
+    NCCL and on CPU tensors with gloo.
     """
 
-    def __init__(self, chunk_steps: int, n_basin: int, device=None, group=None):
+    def __init__(self, chunk_steps: int, n_basin: int, device=None, group=None, exponents=None):
         import torch
 
         self.torch = torch
         self.group = group
         self.n_basin = int(n_basin)
-        self.buffer = torch.zeros(int(chunk_steps), self.n_basin, 3, dtype=torch.float64, device=device)
+        self.chunk_steps = int(chunk_steps)
+        self.buffer = torch.zeros(self.chunk_steps, self.n_basin, 3, dtype=torch.float64, device=device)
+        self.exponents = None if exponents is None else tuple(int(e) for e in exponents)
+        self.accumulator = None
+        if self.exponents is not None:
+            self.accumulator = torch.zeros(self.chunk_steps * self.n_basin * 3 * 2 + 1, dtype=torch.int64, device=device)
+            e = torch.tensor(self.exponents, dtype=torch.float64, device=device)
+            self._scale_hi, self._scale_lo = torch.exp2(e - 40.0), torch.exp2(e - 82.0)
+
+    @property
+    def target(self):
+        """What ``MeltEngine.run(basin_agg=...)`` should accumulate into."""
+        return self.buffer if self.accumulator is None else self.accumulator
+
+    @property
+    def n_left_out(self) -> int:
+        """Exact mode: contributions the kernel left out (non-finite, or beyond 2^E_q); 0 for sane inputs."""
+        return 0 if self.accumulator is None else int(self.accumulator[-1].item())
 
     def zero(self):
         self.buffer.zero_()
+        if self.accumulator is not None:
+            self.accumulator.zero_()
+        return self.target
+
+    def decode(self):
+        """int64 {hi, lo} words -> float64 ``buffer`` (value = hi * 2^(E-40) + lo * 2^(E-82)); a pure function of
+        the integer sums, hence as reproducible as they are."""
+        w = self.accumulator[:-1].view(self.chunk_steps, self.n_basin, 3, 2).to(self.torch.float64)
+        self.torch.add(w[..., 0] * self._scale_hi, w[..., 1] * self._scale_lo, out=self.buffer)
         return self.buffer
 
     def reduce(self, async_op: bool = False):
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if self.accumulator is not None:
+            if multi:
+                dist.all_reduce(self.accumulator, op=dist.ReduceOp.SUM, group=self.group)
+            self.decode()
+            return None
+        if multi:
             return dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         return None
 
