@@ -101,7 +101,9 @@ def main() -> None:
     for f in ("tfg_physics.cuh", "tfg_run.cuh"):
         src[f] = (ROOT / "topoflow_glacier_b200" / "csrc" / f).read_text().splitlines()
     print(f"kernel {a.kernel}: {len(insts)} SASS instructions; {'dynamic' if dyn else 'static'} totals: all={all_t} fp64={all_f}")
-    for book, n in sorted(fp.items(), key=lambda kv: -kv[1])[: a.top]:
+    ranked = fp if all_f else tot  # float32 kernels have no FP64 instructions: rank by all instructions
+    for book, _ in sorted(ranked.items(), key=lambda kv: -kv[1])[: a.top]:
+        n = fp[book]
         f, l = book
         s = src.get(f, [""] * (l + 1))[l - 1].strip()[:90] if f in src else ""
         print(f"{100 * n / max(all_f, 1):5.1f}% fp64 {n:>12} | all {tot[book]:>12} | {f}:{l}  {s}")

@@ -258,7 +258,11 @@ def test_snowfall_window_threshold_knife_edge(mode, cuda_device):
     flips = np.diff((want["snow3day"] >= 0.03).astype(int), axis=0) != 0
     assert flips.sum() > 20
     assert np.array_equal(got["n"], want["n"])
-    assert np.array_equal(got["snow3day"][near], want["snow3day"][near])  # inside the band: the exact re-sum
+    # the decisions above are exact; the recorded total is the exact re-sum inside the kernel's drift band
+    # (~336 roundings of 0.03 in the strict mode, 1e-9 in the fast mode) and the incremental sum outside it
+    np.testing.assert_allclose(got["snow3day"][near], want["snow3day"][near], rtol=0, atol=2e-15)
+    tight = np.abs(want["snow3day"] - 0.03) < 1e-16
+    assert np.array_equal(got["snow3day"][tight], want["snow3day"][tight])
 
 
 @pytest.mark.parametrize("mode", ["f64", "f64_fast", "f32"])

@@ -146,6 +146,13 @@ template <class P> __device__ __forceinline__ Num<P> div3600(Num<P> a) {
       return Num<P>(__fma_rn(__fma_rn(-3600.0, q, a.v), y, q));
     }
     return xdiv(a, Num<P>(3600.0));
+  } else if constexpr (P::f32) {  // the same sequence in float32 (exact residual for |a| >= 2^-60, also under FTZ)
+    if (fabsf(a.v) >= 8.6736174e-19f || a.v == 0.0f) {
+      const float y = 1.0f / 3600.0f;
+      const float q = __fmul_rn(a.v, y);
+      return Num<P>(__fmaf_rn(__fmaf_rn(-3600.0f, q, a.v), y, q));
+    }
+    return zdiv(a, Num<P>(3600.0));
   } else {
     return zdiv(a, Num<P>(3600.0));
   }

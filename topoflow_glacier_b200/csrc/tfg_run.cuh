@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     for (int j = 0; j < slots; ++j) tot = xadd(tot, R(ring[(int64_t)j * N]));
   }
   R tot_hi = nabs(tot);
-  const R guard(P::f32 ? 1e-4 : 1e-9);
+  const R guard(P::f32 ? 1.2e-7 : 2.3e-16);  // two units of round-off per counted operation
+  R n_round((double)slots + 16.0);  // seeding additions + the reference sum's own depth
 
   int basin = 0;
   bool warp_uniform = false;
@@ -315,12 +316,15 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
           // threshold suffices; larger sums (absurd forcing) take the exact path every step
           near_threshold = (nabs(tot - LIT(snow_thr, 0.03)) <= 1e-9) || (__double2hiint(tot.v) >= 0x40c38800);
         } else {
+          // drift bound: (seed additions + 2 per step) roundings of the largest sum seen since the last exact sum
           tot_hi = nmax(tot_hi, nabs(tot));
-          near_threshold = nabs(tot - 0.03) <= guard * nmax(tot_hi, R(1.0));
+          n_round = n_round + R(2.0);
+          near_threshold = nabs(tot - 0.03) <= (guard * n_round) * tot_hi;
         }
         if (near_threshold) {
           tot = window_sum_exact<P>(ring, N, slots, slot);
           tot_hi = nabs(tot);
+          n_round = R(16.0);  // the exact sum itself: 8 lanes of 9 additions + 3 levels, in reference order
         }
         tot_now = tot;
       }
