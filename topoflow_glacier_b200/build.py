@@ -24,7 +24,7 @@ INCLUDE = PKG.parent / "include"
 SOURCES = ["tfg_abi.cu", "tfg_run_strict.cu", "tfg_run_fast.cu", "tfg_run_f32.cu"]
 # float32 kernel: flush-to-zero, so that MUFU.EX2 / LG2 / RCP need no denormal pre- and post-scaling (three extra
 # instructions around each of the ~25 special-function calls of a step); float64 code is unaffected by the flag
-EXTRA_FLAGS = {"tfg_run_f32.cu": ["-ftz=true"]}
+EXTRA_FLAGS = {"tfg_run_f32.cu": ["-ftz=true", "-prec-sqrt=false", "-prec-div=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -278,7 +278,7 @@ TFG_HD float horner32(float x) {
 }
 TFG_HD float rcp32(float b) {
 #if defined(__CUDA_ARCH__)
-  return __frcp_rn(b);
+  return __fdividef(1.0f, b);  // MUFU.RCP, ~1 ulp (the IEEE __frcp_rn costs a Newton step and a slow path)
 #else
   return 1.0f / b;
 #endif
@@ -297,12 +297,23 @@ TFG_HD float asin01_32(float x) {  // 0 <= x <= 1 (clamped)
   const float a = fmaf(s * w, horner32<kAsinP32>(w), s);
   return big ? fmaf(-2.0f, a, 1.5707963267948966f) : a;
 }
+TFG_HD float atan_diff32(float a, float b) {  // atan(a) - atan(b) = atan2(a - b, 1 + a*b), as atan_diff above
+  const float y = a - b, x = fmaf(a, b, 1.0f);
+  const float ay = fabsf(y), ax = fabsf(x);
+  const bool swap = ay > ax;
+  const float hi = swap ? ay : ax, lo = swap ? ax : ay;
+  const float t = (hi > 0.0f) ? lo * rcp32(hi) : 0.0f;
+  float r = t * horner32<kAtanP32>(t * t);
+  r = swap ? 1.5707963267948966f - r : r;
+  r = (x < 0.0f) ? 3.141592653589793f - r : r;
+  return copysignf(r, y);
+}
 TFG_HD float stull_wet_bulb32(float T, float RH) {  // 0 <= RH <= 2
   const float a1 = horner32<kStull132>(RH);
   const float u = 0.023101f * RH;
   const float a4 = u * fmaf(u * u, -1.0f / 3.0f, 1.0f);
   const float t4 = (0.00391838f * (RH * sqrtf(RH))) * a4;
-  return ((((T * a1) + atan32(T + RH)) - atan32(RH - 1.676331f)) + t4) - 4.86035f;
+  return (((T * a1) + atan_diff32(T + RH, RH - 1.676331f)) + t4) - 4.86035f;
 }
 
 }  // namespace fm
