@@ -21,3 +21,4 @@ ARRAY_FN(mc_asin01, asin01(a))
 ARRAY_FN(mc_atan_core, atan_core(a))
 ARRAY_FN(mc_stull, stull_wet_bulb(a, b))
 ARRAY_FN(mc_atan_diff, atan_diff(a, b))
+ARRAY_FN(mc_root7, root7(a, (float)b))

@@ -95,6 +95,17 @@ def test_arctangents_and_wet_bulb(lib):
     assert np.max(np.abs(call(lib, "mc_stull", T, RH).astype(L) - want)) < 5e-14   # |T| * 1 ulp of the arctangent
 
 
+def test_seventh_root(lib):
+    """x**(1/7) by one Householder step from a float32 seed: <= ~8 ulp with the seed's relative error up to 3e-6
+    (MUFU lg2/ex2 deliver ~4e-7)."""
+    rng = np.random.default_rng(5)
+    x = np.exp(rng.uniform(np.log(1e-12), np.log(10.0), 300_000))
+    want = x.astype(L) ** (L(1) / L(7))
+    for scale, bound in ((1.0, 8.0), (1 + 1e-6, 9.0), (1 - 1e-6, 9.0), (1 + 3e-6, 32.0)):
+        got = call(lib, "mc_root7", x, np.full(x.size, scale))
+        assert float(np.max(np.abs((got.astype(L) - want) / want))) < bound * 2.3e-16, scale
+
+
 def test_markstein_division_by_3600_is_correctly_rounded():
     """q = a*y, r = fma(-3600, q, a), q' = fma(r, y, q), y = RN(1/3600)  ==  RN(a/3600)  (tfg_num.cuh div3600)."""
     rng = np.random.default_rng(4)

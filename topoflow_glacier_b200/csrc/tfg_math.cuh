@@ -42,12 +42,13 @@ inline double mk64(int hi, int lo) {
 // instruction and stay inline.
 struct MathLit {
   double exp_scale, exp_nl2h, exp_nl2l, ln2h, ln2l, pio2h, pio2l, pih, pil, tiny, st_u, st_c9, st_c7, st_c5, st_c3,
-      st_d, st_c, st_f;
+      st_d, st_c, st_f, r7_c1, r7_c2;
 };
 __constant__ MathLit kML = {92.332482616893656877, -1.08304246932675596327e-02, -2.98158582698529328128e-12,
                             6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.5707963267948966,
                             6.123233995736766e-17, 3.141592653589793, 1.2246467991473532e-16, 1e-290, 0.023101,
-                            1.0 / 9.0, -1.0 / 7.0, 0.2, -1.0 / 3.0, 0.00391838, 1.676331, 4.86035};
+                            1.0 / 9.0, -1.0 / 7.0, 0.2, -1.0 / 3.0, 0.00391838, 1.676331, 4.86035, 1.0 / 7.0,
+                            4.0 / 49.0};
 
 template <int N>
 TFG_HD double horner(const double (&c)[N], double x) {
@@ -218,6 +219,28 @@ TFG_HD double log_tab(double x) {
   const double pa = fma(r2, fma(r2, a2, a1), a0);
   const double lo = fma(r2, pa, fma(ed, kML.ln2l, r));
   return w + lo;
+}
+
+// x**(1/7) for 1e-30 < x < 1e30 (the Brutsaert emissivity, reference bmi_topoflow_glacier.py:1179): a float32
+// MUFU seed of w = x**(-1/7) (relative error d <= ~1e-6), ONE third-order Householder step on f(w) = w**-7 - x
+// (no division: e = 1 - x w**7, w <- w (1 + e/7 + 4 e*e/49), error 20 d**3), then x**(1/7) = x w**6.
+// 12 FP64 instructions instead of the 24 of exp(log(x)/7).  `seed_scale` perturbs the seed (host tests only).
+TFG_HD double root7(double x, float seed_scale = 1.0f) {
+  float w0f;
+#if defined(__CUDA_ARCH__)
+  asm("{ .reg .f32 l; lg2.approx.ftz.f32 l, %1; mul.f32 l, l, 0fBE124925; ex2.approx.ftz.f32 %0, l; }"
+      : "=f"(w0f) : "f"((float)x));   // 0fBE124925 = -1/7
+  w0f *= seed_scale;
+#else
+  w0f = exp2f(log2f((float)x) * (-1.0f / 7.0f)) * seed_scale;
+#endif
+  const double w0 = (double)w0f;
+  const double w2 = w0 * w0, w4 = w2 * w2;
+  const double w7 = (w4 * w2) * w0;
+  const double e = fma(-x, w7, 1.0);
+  const double w1 = fma(w0, e * fma(e, kML.r7_c2, kML.r7_c1), w0);
+  const double v2 = w1 * w1, v4 = v2 * v2;
+  return x * (v4 * v2);
 }
 
 // asin(x) for 0 <= x <= 1 (values slightly above 1 are clamped)

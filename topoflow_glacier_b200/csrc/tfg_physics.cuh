@@ -332,7 +332,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if (!k.satterlund) {
     R x;
     if constexpr (P::lean) x = (e_air * LIT(c01, 0.1)) * rTK; else x = divk(e_air, 10.0) / T_K;
-    const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
+    R term1;
+    if constexpr (P::lean) term1 = R(k.emis_a) * R(fm::root7(x.v));   // x > 0 on the sane path
+    else term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
     em_air = (term1 * R(k.emis_b)) + R(k.canopy);
   } else {
     em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, divk(T_K, 2016.0))));
