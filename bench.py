@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "cell_timesteps_per_sec"
 UNIT = "cell-steps/s"
 GRID_CELLS = 4096 * 4096
+REGIONAL_CELLS = 100_000_000
 N_BASIN = 4096
 
 
@@ -177,8 +178,11 @@ def run_reference_arm(args):
         if i >= args.warmup:
             times.append((thr, wall))
     cs = n_cells * n_steps
-    wall = sum(w for _, w in times)
-    value = cs * len(times) / wall
+    # like the GPU arm (device time, max over ranks): the slowest worker's compute time per step, not the wall
+    # clock around fork + pickling of the sample
+    busy = sum(cs / thr for thr, _ in times)
+    value = cs * len(times) / busy
+    wall = busy
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(times), "higher_is_better": True, "scaling": "weak",
@@ -186,7 +190,8 @@ def run_reference_arm(args):
         "config": {"workload": "synthetic glacierised raster (cfg-4 distributions), CPU sample", "cells": n_cells,
                    "timesteps_per_step": n_steps},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_cells} cells x {n_steps} timesteps per step, oracle/np_ref.py, one process per core"},
+                         "sample": f"{n_cells} cells x {n_steps} timesteps per step, oracle/np_ref.py, one process per core; "
+                                   "timed as the slowest worker's compute time (pool start-up and pickling excluded)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,13 +231,22 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_cells, Tc, mode = args.cells, args.chunk, args.mode
+    Tc, mode = args.chunk, args.mode
+    regional = args.workload == "regional"
+    if regional:  # strong scaling: the grid is fixed, every rank owns a contiguous 128-aligned block of it
+        from topoflow_glacier_b200.sharding import shard_bounds
+
+        total_cells = args.cells
+        lo, hi = shard_bounds(total_cells, world, rank)
+        n_cells, first_cell = hi - lo, lo
+    else:         # weak scaling: one raster per GPU
+        n_cells, first_cell, total_cells = args.cells, rank * args.cells, args.cells * world
     es = 4 if mode == "f32" else 8
     consts = default_constants()
-    tabs = synthetic_cells(n_cells, seed=4096 + rank, device=dev)
-    raw_attrs = tabs.pop("raw")
-    per_basin = -(-n_cells * world // N_BASIN)
-    basin_id = ((torch.arange(n_cells, device=dev, dtype=torch.int64) + rank * n_cells) // per_basin).to(torch.int32)
+    tabs = synthetic_cells(n_cells, seed=(100 if regional else 4096) + rank, device=dev)
+    raw_attrs = {"elev": tabs.pop("raw")["elev"]}
+    per_basin = -(-total_cells // N_BASIN)  # 24 415 cells per basin on the regional grid (SURVEY.md 8d cfg 5)
+    basin_id = ((torch.arange(n_cells, device=dev, dtype=torch.int64) + first_cell) // per_basin).to(torch.int32)
     horizon = (args.warmup + args.steps + 4) * Tc + (args.e2e_steps + args.warmup + 2) * args.e2e_chunk + 64
     eng = MeltEngine(None, consts, "2012100100", dt_hours=1, zones=[-8.0], basin_id=basin_id, n_basin=N_BASIN,
                      mode=mode, device=local_rank, horizon_steps=horizon, device_statics=tabs)
@@ -301,8 +315,8 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
-    cell_steps = n_cells * Tc
-    value = world * cell_steps * args.steps / (dev_ms * 1e-3)
+    cell_steps = n_cells * Tc  # this rank's launch
+    value = total_cells * Tc * args.steps / (dev_ms * 1e-3)
 
     # ---- same launch on spatially coherent weather (precipitation shared by 4096 consecutive cells) --------------
     # The headline above uses per-cell independent precipitation: the worst case for warp divergence
@@ -327,6 +341,9 @@ def run_gpu_arm(args):
 
     # ---- end to end through the public API with host buffers -----------------------------------------------
     Te = args.e2e_chunk
+    if regional:  # keep only the block the e2e leg streams; the 64 GB kernel-leg chunk goes back to the allocator
+        forcing = forcing[:Te].clone()
+        torch.cuda.empty_cache()
     raw_dtype = torch.float32 if args.e2e_raw == "float32" else torch.float64
     raw_host = torch.empty(Te, 6, n_cells, dtype=raw_dtype).pin_memory()
     # raw met columns derived from the synthetic chunk (mm/h, K, Pa, kg/kg, U, V)
@@ -377,7 +394,7 @@ def run_gpu_arm(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_cells * Te * args.e2e_steps / float(t.item())
+    e2e_value = total_cells * Te * args.e2e_steps / float(t.item())
     h2d = raw_host.numel() * raw_host.element_size()
     d2h = out_host[0].numel() * out_host[0].element_size() + agg_host[0].numel() * 8
 
@@ -408,10 +425,13 @@ def run_gpu_arm(args):
                 compute = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if regional else "weak",
+            "vs_baseline": None,
             "dtype": "f32" if mode == "f32" else "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 4096x4096 glacierised raster per GPU (BASELINE configs[3]), hourly forcing",
-                       "cells_per_gpu": n_cells, "timesteps_per_step": Tc, "arithmetic_mode": mode,
+            "config": {"workload": ("synthetic 100M-cell regional grid sharded over the GPUs (BASELINE configs[4]), hourly forcing"
+                                    if regional else
+                                    "synthetic 4096x4096 glacierised raster per GPU (BASELINE configs[3]), hourly forcing"),
+                       "cells_total": total_cells, "cells_per_gpu": n_cells, "timesteps_per_step": Tc, "arithmetic_mode": mode,
                        "basin_aggregates": N_BASIN, "aggregate_sums": args.agg, "forcing": "device-resident chunk, Philox synthetic, reused each step",
                        "l2": f"inputs {es * 5 * cell_steps / 1e9:.1f} GB per launch >> 126 MB L2 (no flush needed)",
                        "parallelism": f"cells sharded x{world}, all_reduce of basin aggregates"},
@@ -442,8 +462,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="f64_fast", choices=["f64", "f64_fast", "f32"])
-    ap.add_argument("--cells", type=int, default=GRID_CELLS)
-    ap.add_argument("--chunk", type=int, default=128, help="timesteps per launch")
+    ap.add_argument("--workload", default="raster", choices=["raster", "regional"],
+                    help="raster: 4096x4096 cells PER GPU (BASELINE configs[3], weak scaling); regional: 100 M cells in "
+                         "total, sharded over the GPUs (configs[4], strong scaling, 16 timesteps per launch)")
+    ap.add_argument("--cells", type=int, default=0, help="cells per GPU (raster) / in total (regional)")
+    ap.add_argument("--chunk", type=int, default=0, help="timesteps per launch (default 128 raster, 16 regional)")
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-raw", default="float32", choices=["float32", "float64"])
@@ -456,6 +479,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    regional = args.workload == "regional"
+    args.cells = args.cells or (REGIONAL_CELLS if regional else GRID_CELLS)
+    args.chunk = args.chunk or (16 if regional else 128)
+    if regional:  # 100 M cells fill the HBM of one GPU: no second forcing realisation, one-timestep e2e blocks
+        args.no_coherent, args.no_cpu, args.e2e_chunk = True, True, 1
     return run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args)
 
 

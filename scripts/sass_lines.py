@@ -101,7 +101,7 @@ def main() -> None:
     for f in ("tfg_physics.cuh", "tfg_run.cuh"):
         src[f] = (ROOT / "topoflow_glacier_b200" / "csrc" / f).read_text().splitlines()
     print(f"kernel {a.kernel}: {len(insts)} SASS instructions; {'dynamic' if dyn else 'static'} totals: all={all_t} fp64={all_f}")
-    ranked = fp if all_f else tot  # float32 kernels have no FP64 instructions: rank by all instructions
+    ranked = fp if all_f > 0.05 * all_t else tot  # float32 kernels have (almost) no FP64 instructions: rank by all
     for book, _ in sorted(ranked.items(), key=lambda kv: -kv[1])[: a.top]:
         n = fp[book]
         f, l = book

@@ -243,6 +243,41 @@ def test_exact_basin_aggregates_are_order_and_sharding_independent(cuda_device):
             np.testing.assert_allclose(got[t, :, j], want, rtol=1e-13, atol=1e-20)
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_long_run_is_split_into_launches_transparently(exact, cuda_device):
+    """A run longer than one launch's 128 clock rows (tfg_run splits it): recorded series, basin aggregates (float
+    and fixed-point) and final state equal those of caller-side pieces of 100 + 100 + 88 steps, bit for bit."""
+    import torch
+
+    from topoflow_glacier_b200.sharding import BasinAggregates
+
+    case = load_case("cats288")
+    T = case["forcing"].shape[0]
+    assert T > 2 * 128
+    f = torch.as_tensor(case["forcing"]).cuda()
+    basin = np.array([0, 0, 1, 1], dtype=np.int32)
+
+    def run(pieces):
+        eng = make_engine(case, mode="f64_fast", basin_id=basin, n_basin=2)
+        recs, aggs, done = [], [], 0
+        for n in pieces:
+            agg = BasinAggregates(n, 2, device=cuda_device, exponents=eng.agg_exponents() if exact else None)
+            recs.append(eng.run(f[done:done + n].contiguous(), n, record=("M_total", "h_swe"), basin_agg=agg.zero()))
+            agg.reduce()
+            aggs.append(agg.buffer.clone())
+            done += n
+        torch.cuda.synchronize()
+        out = (torch.cat([r["M_total"] for r in recs]), torch.cat([r["h_swe"] for r in recs]), torch.cat(aggs),
+               eng.state.clone(), eng.ring.clone())
+        eng.close()
+        return out
+
+    whole, parts = run([T]), run([100, 100, T - 200])
+    for a, b in zip(whole, parts):
+        assert torch.equal(a, b)
+    assert float(whole[2][:, :, 1].abs().sum()) > 0
+
+
 def test_checkpoint_resume_is_bit_identical(tmp_path, cuda_device):
     """state + snowfall window + step counter saved mid-run, resumed in a fresh model == uninterrupted run."""
     import torch

@@ -221,6 +221,89 @@ TFG_HD double log_tab(double x) {
   return w + lo;
 }
 
+// ---- N independent arguments at once -----------------------------------------------------------------------
+// ptxas schedules the melt kernel for register pressure (96 registers), which serialises the elementary functions:
+// a warp then issues one dependent FP64 chain at a time and waits out the pipe latency between instructions
+// (ncu: `wait` is the top stall).  These variants evaluate N independent arguments stage by stage, so the N chains
+// are adjacent in program order and overlap in the FP64 pipe.
+template <int N>
+TFG_HD void rcp3_n(const double (&b)[N], double (&r)[N]) {
+  double e[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#if defined(__CUDA_ARCH__)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(b[i]));
+#else
+    r[i] = rcp_seed_host(b[i]);
+#endif
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-b[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(e[i], e[i], e[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(r[i], e[i], r[i]);
+}
+
+template <int N>
+TFG_HD void exp_tab_n(const double (&x)[N], double (&y)[N]) {
+  double t[N], fn[N], r[N], T[N], r2[N], a[N], b[N];
+  int k[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fma(x[i], kML.exp_scale, 6755399441055744.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { k[i] = lo32(t[i]); fn[i] = t[i] - 6755399441055744.0; }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r[i] = fma(fn[i], kML.exp_nl2h, x[i]); T[i] = TFG_EXPTAB(k[i] & 63); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(fn[i], kML.exp_nl2l, r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    r2[i] = r[i] * r[i];
+    a[i] = fma(r[i], TFG_COEF(kExpTQ, 2), TFG_COEF(kExpTQ, 3));
+    b[i] = fma(r[i], TFG_COEF(kExpTQ, 0), TFG_COEF(kExpTQ, 1));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) a[i] = fma(r2[i], b[i], a[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) a[i] = fma(r2[i], a[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double v = fma(T[i], a[i], T[i]);
+    y[i] = mk64(hi32(v) + ((k[i] >> 6) << 20), lo32(v));
+  }
+}
+
+template <int N>
+TFG_HD void log_tab_n(const double (&x)[N], double (&y)[N]) {
+  double z[N], invc[N], logc[N], r[N], ed[N], w[N], r2[N], a0[N], a1[N], a2[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int hi = hi32(x[i]);
+    const int tmp = hi - 0x3fe60000;
+    const int j = (tmp >> 13) & 127;
+    z[i] = mk64(hi - (tmp & (int)0xfff00000), lo32(x[i]));
+    invc[i] = TFG_LOGTAB(j, 0);
+    logc[i] = TFG_LOGTAB(j, 1);
+    ed[i] = (double)(tmp >> 20);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { r[i] = fma(z[i], invc[i], -1.0); w[i] = fma(ed[i], kML.ln2h, logc[i]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    r2[i] = r[i] * r[i];
+    a0[i] = fma(r[i], TFG_COEF(kLogTA, 4), TFG_COEF(kLogTA, 5));
+    a1[i] = fma(r[i], TFG_COEF(kLogTA, 2), TFG_COEF(kLogTA, 3));
+    a2[i] = fma(r[i], TFG_COEF(kLogTA, 0), TFG_COEF(kLogTA, 1));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) { a1[i] = fma(r2[i], a2[i], a1[i]); ed[i] = fma(ed[i], kML.ln2l, r[i]); }
+#pragma unroll
+  for (int i = 0; i < N; ++i) a0[i] = fma(r2[i], a1[i], a0[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = w[i] + fma(r2[i], a0[i], ed[i]);
+}
+
 // x**(1/7) for 1e-30 < x < 1e30 (the Brutsaert emissivity, reference bmi_topoflow_glacier.py:1179): a float32
 // MUFU seed of w = x**(-1/7) (relative error d <= ~1e-6), ONE third-order Householder step on f(w) = w**-7 - x
 // (no division: e = 1 - x w**7, w <- w (1 + e/7 + 4 e*e/49), error 20 d**3), then x**(1/7) = x w**6.

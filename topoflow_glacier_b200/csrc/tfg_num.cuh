@@ -140,7 +140,7 @@ template <class P> __device__ __forceinline__ Num<P> zdiv(Num<P> a, Num<P> b) {
 template <class P> __device__ __forceinline__ Num<P> div3600(Num<P> a) {
   if constexpr (P::lean) {
     const unsigned hi = (unsigned)__double2hiint(a.v) & 0x7fffffffu;
-    if (hi >= 0x04100000u || a.v == 0.0) {
+    if (hi >= 0x04100000u || (hi | (unsigned)__double2loint(a.v)) == 0u) {
       const double y = 1.0 / 3600.0;
       const double q = __dmul_rn(a.v, y);
       return Num<P>(__fma_rn(__fma_rn(-3600.0, q, a.v), y, q));

@@ -175,11 +175,20 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   // Atmospheric_Transmissivity solar_funcs.py:608-614
   const R a_sa = LIT(sa_a0, -0.1240) - (LIT(sa_a1, 0.0207) * W_p);
   const R b_sa = LIT(sa_b0, -0.0682) - (LIT(sa_b1, 0.0248) * W_p);
-  const R tau = nmin(relu(nexp(a_sa + (b_sa * M_opt)) - R(k.dust)), R(1.0));
   // Scattering_Attenuation solar_funcs.py:649-653
   const R a_s = LIT(s_a0, -0.0363) - (LIT(s_a1, 0.0084) * W_p);
   const R b_s = LIT(s_b0, -0.0572) - (LIT(s_b1, 0.0173) * W_p);
-  const R gam_s = (R(1.0) - nexp(a_s + (b_s * M_opt))) + R(k.dust);
+  R e_tau, e_gam;
+  if constexpr (P::lean) {  // the two exponentials side by side (see fm::exp_tab_n)
+    const double ex[2] = {(a_sa + (b_sa * M_opt)).v, (a_s + (b_s * M_opt)).v};
+    double ey[2];
+    fm::exp_tab_n<2>(ex, ey);
+    e_tau = R(ey[0]); e_gam = R(ey[1]);
+  } else {
+    e_tau = nexp(a_sa + (b_sa * M_opt)); e_gam = nexp(a_s + (b_s * M_opt));
+  }
+  const R tau = nmin(relu(e_tau - R(k.dust)), R(1.0));
+  const R gam_s = (R(1.0) - e_gam) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
   const R K_h = relu(isc_e0 * (((cos_d * R(s.get(kSCosLat))) * c_wt) + (sin_d * R(s.get(kSSinLat)))));
@@ -229,43 +238,56 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // dividing by exp(x), and the aerodynamic block (:640-733) collapses into one quotient:
     //   stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
     //   unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
-    rTK = R(fm::rcp3(T_K.v));
-    const R inv_p0 = nexp(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)) * R(k.inv_p0c);   // :551-556
-    const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));                             // :817
+    // Independent reciprocals / exponentials / logarithms are evaluated side by side (fm::*_n) so that their
+    // dependent FP64 chains overlap.  SATTERLUND configurations never get here (the kernel runs them strictly).
+    // -- three reciprocals: 1/T_K, the vapour-pressure quotient (:817), the Magnus quotient of the air (:788)
+    const double den3[3] = {T_K.v, (R(k.eps) + (R(k.one_m_eps) * q)).v, (T_air + LIT(mag_b, 237.3)).v};
+    double rc3[3];
+    fm::rcp3_n<3>(den3, rc3);
+    rTK = R(rc3[0]);
+    const R e = (q * P_air) * R(rc3[1]);
     e_air = e * LIT(c001, 0.01);
-    R en(1.0);
-    if (!k.satterlund) {
-      const R t1a = (LIT(mag_a, 17.3) * T_air) / (T_air + LIT(mag_b, 237.3));                // :788
-      en = nexp(-t1a);
-      RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                               // e_air / (6.11 exp(t1)), :838
-    } else {
-      e_sat_air = e_sat_mbar<P>(k, T_air);                                                   // :794-796
-      RH = e_air / e_sat_air;
-    }
-    const R log_term = nlog(e_air * LIT(inv_dew_a, 0.1636098885816659));                    // log(e_air / 6.1121), :892
-    T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
+    // -- exp(-M g elev / (R* T_K)) (:551-556), exp(-17.3 T/(T+237.3)); log(e_air/6.1121) (:892), the log law (:670)
+    const double ex2[2] = {(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)).v, (-((LIT(mag_a, 17.3) * T_air) * R(rc3[2]))).v};
+    const double lx2[2] = {(e_air * LIT(inv_dew_a, 0.1636098885816659)).v,
+                           nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)).v};
+    double ey2[2], ly2[2];
+    fm::exp_tab_n<2>(ex2, ey2);
+    fm::log_tab_n<2>(lx2, ly2);
+    const R inv_p0 = R(ey2[0]) * R(k.inv_p0c);
+    const R en(ey2[1]);
+    RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                                 // e_air / (6.11 exp(t1)), :838
+    const R log_term(ly2[0]), L(ly2[1]);
+    T_dew = (LIT(dew_c, 257.14) * log_term) * R(fm::rcp3((LIT(dew_b, 18.678) - log_term).v));
     const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
     T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);                                         // :906-911
-    e_sat_surf = e_sat_mbar<P>(k, T_surf);
     dT = T_air - T_surf;
     const R top = R(k.gz) * dT;                                                              // :640-644
     R bot = (uz * uz) * T_K;
     bot = sel(bot == 0.0, LIT(c001, 0.01), bot);
-    const R L = nlog(nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)));                        // :670
     const bool stable = top > 0.0;
     const R ten_top = R(10.0) * top;
     const R num = sel(stable, bot, bot - ten_top);
     const R den = sel(stable, bot + ten_top, bot);
     const R uk2 = uz * R(k.kappa2);
     const R LL = L * L;
-    Dh = (uk2 * num) / (LL * den);
+    // -- two reciprocals: the Magnus quotient of the surface, the aerodynamic quotient
+    const double den2[2] = {(T_surf + LIT(mag_b, 237.3)).v, (LL * den).v};
+    double rc2[2];
+    fm::rcp3_n<2>(den2, rc2);
+    Dh = (uk2 * num) * R(rc2[1]);
+    // -- W_p = 1.12 exp(0.0614 T_dew) (:919-920) and e_sat(T_surf) (:784-802)
+    const double ex2b[2] = {(LIT(wp_b, 0.0614) * T_dew).v, ((LIT(mag_a, 17.3) * T_surf) * R(rc2[0])).v};
+    double ey2b[2];
+    fm::exp_tab_n<2>(ex2b, ey2b);
+    W_p = LIT(wp_a, 1.12) * R(ey2b[0]);
+    e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
     Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
-    W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);                                 // :919-920
     e_surf = RH * e_sat_surf;                                                                // :853
     Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) * inv_p0);                  // :931-934
     // only read when a caller records them (dead code otherwise)
     p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
-    if (!k.satterlund) e_sat_air = LIT(esat10, 6.11) / en;
+    e_sat_air = LIT(esat10, 6.11) / en;
   } else {
     // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
     p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));
@@ -329,7 +351,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R Qn_SW = K_cs * (R(1.0) - albedo);
   // ---- update_em_air :1167-1192
   R em_air;
-  if (!k.satterlund) {
+  if (P::lean || !k.satterlund) {
     R x;
     if constexpr (P::lean) x = (e_air * LIT(c01, 0.1)) * rTK; else x = divk(e_air, 10.0) / T_K;
     R term1;

@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
                         (((unsigned)__double2hiint(f1) & 0x7fffffffu) < (unsigned)__double2hiint(90.0)) &&
                         in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
                         (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
-      if (__all_sync(0xffffffffu, sane && state_ok)) {
+      // (SATTERLUND = True, a rarely used configuration switch, also takes the strict step: the lean one is
+      // written for the default Magnus / Brutsaert formulas only, which keeps it free of configuration branches)
+      if (__all_sync(0xffffffffu, sane && state_ok) && !p.k.satterlund) {
         cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
       } else {
         // Same step in the strict arithmetic (libdevice, IEEE division, NumPy's NaN rules): whatever the input
