@@ -416,7 +416,14 @@ def run_gpu_arm(args):
                 mix = json.loads(mp.read_text())[mode]
                 # ceiling = measured DFMA thread-ops/s / FP64 instructions per cell-step (a warp-instruction is 32 of them)
                 ceiling = fp64_peak / mix["fp64_warp_inst_per_warp_step"]
+                # issue ceiling: one warp-instruction per cycle and scheduler (4 per SM)
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+                issue_ceiling = sms * 4 * mhz * 1e6 * 32 / mix["warp_inst_per_warp_step"]
                 compute = {"bound": "fp64_pipe", "fp64_warp_inst_per_warp_step": mix["fp64_warp_inst_per_warp_step"],
+                           "warp_inst_per_warp_step": mix["warp_inst_per_warp_step"],
+                           "issue_ceiling_cell_steps_per_s": issue_ceiling,
+                           "frac_of_issue_ceiling": (cell_steps / (kern_ms * 1e-3)) / issue_ceiling,
                            "fp64_peak_tflops_measured": 2 * fp64_peak / 1e12,
                            "ceiling_cell_steps_per_s": ceiling, "frac_of_ceiling": (cell_steps / (kern_ms * 1e-3)) / ceiling,
                            "ncu_fp64_pipe_active_pct": mix["fp64_pipe_active_pct"],

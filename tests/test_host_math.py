@@ -49,6 +49,15 @@ def test_exp(lib):
     assert ulps(call(lib, "mc_exp_core", x), want) < 1.2
 
 
+def test_n_at_once_variants_equal_scalar_routines(lib):
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-50, 50, 6000)
+    assert np.array_equal(call(lib, "mc_exp_tab", x), call(lib, "mc_exp_tab_2", x))
+    x = np.exp(x)
+    assert np.array_equal(call(lib, "mc_log_tab", x), call(lib, "mc_log_tab_2", x))
+    assert np.array_equal(call(lib, "mc_rcp3", x), call(lib, "mc_rcp3_3", x))
+
+
 def test_log(lib):
     rng = np.random.default_rng(1)
     x = np.concatenate([np.exp(rng.uniform(-700, 700, 200_000)), rng.uniform(0.5, 2, 400_000),
