@@ -111,6 +111,33 @@ def test_single_steps_equal_fused_run(mode, cuda_device):
         e.close()
 
 
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_kernel_instantiations_agree_bit_for_bit(mode, cuda_device):
+    """Recording, basin aggregates and the diagnostic integrals select different template instantiations of the
+    kernel.  None of them may change the state: the strict mode uses single-rounding intrinsics throughout, the fast
+    float64 unit is compiled with -fmad=false and spells out every fused multiply-add (tfg_num.cuh fmadd)."""
+    import torch
+
+    case = load_case("rand64")
+    f = torch.as_tensor(case["forcing"]).to(cuda_device)
+    T, N = f.shape[0], case["N"]
+    basin = (np.arange(N) // 8).astype(np.int32)
+    plain = make_engine(case, mode=mode)
+    plain.run(f)
+    rec = make_engine(case, mode=mode)
+    rec.run(f, record=REC)
+    agg = make_engine(case, mode=mode, basin_id=basin, n_basin=int(basin.max()) + 1)
+    agg.run(f, basin_agg=torch.zeros(T, int(basin.max()) + 1, 3, dtype=torch.float64, device=cuda_device))
+    novol = make_engine(case, mode=mode, diag_integrals=False)
+    novol.run(f)
+    torch.cuda.synchronize()
+    for other in (rec, agg):
+        assert torch.equal(plain.state, other.state) and torch.equal(plain.ring, other.ring)
+    assert torch.equal(plain.state[:12], novol.state[:12]) and torch.equal(plain.ring, novol.ring)
+    for e in (plain, rec, agg, novol):
+        e.close()
+
+
 def test_f32_mode_tolerance(cuda_device):
     """fp32 mode has its own, looser, stated tolerance (DESIGN.md "fp32 mode").
 

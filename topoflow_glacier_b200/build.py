@@ -24,7 +24,9 @@ INCLUDE = PKG.parent / "include"
 SOURCES = ["tfg_abi.cu", "tfg_run_strict.cu", "tfg_run_fast.cu", "tfg_run_f32.cu"]
 # float32 kernel: flush-to-zero, so that MUFU.EX2 / LG2 / RCP need no denormal pre- and post-scaling (three extra
 # instructions around each of the ~25 special-function calls of a step); float64 code is unaffected by the flag
-EXTRA_FLAGS = {"tfg_run_f32.cu": ["-ftz=true", "-prec-sqrt=false", "-prec-div=false"]}
+# fast float64 kernel: no implicit contraction -- every fused multiply-add is written out (fmadd / fma), so all template
+# instantiations (recording, aggregates, TMA staging) evaluate exactly the same arithmetic and agree bit for bit
+EXTRA_FLAGS = {"tfg_run_f32.cu": ["-ftz=true", "-prec-sqrt=false", "-prec-div=false"], "tfg_run_fast.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -74,6 +74,21 @@ TFG_CMP(<) TFG_CMP(<=) TFG_CMP(>) TFG_CMP(>=) TFG_CMP(==) TFG_CMP(!=)
 
 template <class P> __device__ __forceinline__ Num<P> sel(bool c, Num<P> a, Num<P> b) { return c ? a : b; }
 
+// a*b + c and c - a*b.  Strict: the two roundings of the reference, in its order.  Fast modes: ONE fused operation,
+// written out because the fast float64 translation unit is compiled with -fmad=false: which multiply-adds are fused
+// is then decided here and not per template instantiation by the compiler, so recording kernels, aggregate kernels
+// and TMA kernels of the fast mode return bit-identical state.
+template <class P> __device__ __forceinline__ Num<P> fmadd(Num<P> a, Num<P> b, Num<P> c) {
+  if constexpr (P::strict) return Num<P>(__dadd_rn(__dmul_rn(a.v, b.v), c.v));
+  else if constexpr (P::f32) return Num<P>(fmaf(a.v, b.v, c.v));
+  else return Num<P>(fma(a.v, b.v, c.v));
+}
+template <class P> __device__ __forceinline__ Num<P> fnmadd(Num<P> a, Num<P> b, Num<P> c) {
+  if constexpr (P::strict) return Num<P>(__dsub_rn(c.v, __dmul_rn(a.v, b.v)));
+  else if constexpr (P::f32) return Num<P>(fmaf(-a.v, b.v, c.v));
+  else return Num<P>(fma(-a.v, b.v, c.v));
+}
+
 // np.minimum / np.maximum propagate NaN; fmin/fmax do not.  Strict mode keeps NumPy's behaviour.
 template <class P> __device__ __forceinline__ Num<P> nmax(Num<P> a, Num<P> b) {
   if constexpr (P::strict) return Num<P>((a.v >= b.v) ? a.v : ((b.v > a.v) ? b.v : a.v + b.v));

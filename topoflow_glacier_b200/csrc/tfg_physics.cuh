@@ -130,8 +130,8 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
     // omega*th = A_t - B_c with A_t = omega*((clock-12)-TE) (host, per step) and B_c = omega*LC (per cell):
     // cos(A - B) = cosA cosB + sinA sinB -- two FMAs instead of a full-range cos()
     const R cA(tr.cos_hour), sA(tr.sin_hour);
-    c_wt = (cA * R(s.get(kSCB))) + (sA * R(s.get(kSSB)));
-    c_u = (cA * R(s.get(kSCB2))) + (sA * R(s.get(kSSB2)));
+    c_wt = fmadd(cA, R(s.get(kSCB)), sA * R(s.get(kSSB)));
+    c_u = fmadd(cA, R(s.get(kSCB2)), sA * R(s.get(kSSB2)));
   }
   // sunrise / sunset arguments, solar_funcs.py:325-326 (horizontal) and :796 (equivalent latitude)
   R arg_eq = R(s.get(kSNegTanEq)) * tan_d, arg_h = R(s.get(kSNegTanLat)) * tan_d;
@@ -156,7 +156,9 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   if (dark) return R(0.0);                                   // solar_funcs.py:940-941
 
   // Zenith_Angle solar_funcs.py:281-284
-  const R cosZ = (R(s.get(kSSinLat)) * sin_d) + ((R(s.get(kSCosLat)) * cos_d) * c_wt);
+  R cosZ;
+  if constexpr (P::strict) cosZ = (R(s.get(kSSinLat)) * sin_d) + ((R(s.get(kSCosLat)) * cos_d) * c_wt);
+  else cosZ = fmadd(R(s.get(kSCosLat)) * cos_d, c_wt, R(s.get(kSSinLat)) * sin_d);
   // Optical_Air_Mass solar_funcs.py:549-568 (Kasten & Young 1989)
   R gamma, t1, t2;
   if constexpr (P::strict) {
@@ -168,36 +170,37 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   } else {
     // elevation angle gamma = 90deg - Z = asin(cos Z), sin(gamma) = cos Z; a/(gamma+b)^c = a*exp(-c*log(gamma+b))
     t1 = relu(cosZ);
-    gamma = nasin01(t1) * R(k.rad2deg);
-    t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(gamma + LIT(ky_b, 6.07995)));
+    const R elev_rad = nasin01(t1);
+    gamma = elev_rad * R(k.rad2deg);
+    t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(fmadd(elev_rad, R(k.rad2deg), LIT(ky_b, 6.07995))));
   }
   const R M_opt = R(1.0) / (t1 + t2);
   // Atmospheric_Transmissivity solar_funcs.py:608-614
-  const R a_sa = LIT(sa_a0, -0.1240) - (LIT(sa_a1, 0.0207) * W_p);
-  const R b_sa = LIT(sa_b0, -0.0682) - (LIT(sa_b1, 0.0248) * W_p);
+  const R a_sa = fnmadd(LIT(sa_a1, 0.0207), W_p, LIT(sa_a0, -0.1240));
+  const R b_sa = fnmadd(LIT(sa_b1, 0.0248), W_p, LIT(sa_b0, -0.0682));
   // Scattering_Attenuation solar_funcs.py:649-653
-  const R a_s = LIT(s_a0, -0.0363) - (LIT(s_a1, 0.0084) * W_p);
-  const R b_s = LIT(s_b0, -0.0572) - (LIT(s_b1, 0.0173) * W_p);
+  const R a_s = fnmadd(LIT(s_a1, 0.0084), W_p, LIT(s_a0, -0.0363));
+  const R b_s = fnmadd(LIT(s_b1, 0.0173), W_p, LIT(s_b0, -0.0572));
   R e_tau, e_gam;
   if constexpr (P::lean) {  // the two exponentials side by side (see fm::exp_tab_n)
-    const double ex[2] = {(a_sa + (b_sa * M_opt)).v, (a_s + (b_s * M_opt)).v};
+    const double ex[2] = {fmadd(b_sa, M_opt, a_sa).v, fmadd(b_s, M_opt, a_s).v};
     double ey[2];
     fm::exp_tab_n<2>(ex, ey);
     e_tau = R(ey[0]); e_gam = R(ey[1]);
   } else {
-    e_tau = nexp(a_sa + (b_sa * M_opt)); e_gam = nexp(a_s + (b_s * M_opt));
+    e_tau = nexp(fmadd(b_sa, M_opt, a_sa)); e_gam = nexp(fmadd(b_s, M_opt, a_s));
   }
   const R tau = nmin(relu(e_tau - R(k.dust)), R(1.0));
   const R gam_s = (R(1.0) - e_gam) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
-  const R K_h = relu(isc_e0 * (((cos_d * R(s.get(kSCosLat))) * c_wt) + (sin_d * R(s.get(kSSinLat)))));
-  const R K_s = relu(isc_e0 * (((cos_d * R(s.get(kSCosEq))) * c_u) + (R(s.get(kSSinEq)) * sin_d)));
+  const R K_h = relu(isc_e0 * fmadd(cos_d * R(s.get(kSCosLat)), c_wt, sin_d * R(s.get(kSSinLat))));
+  const R K_s = relu(isc_e0 * fmadd(cos_d * R(s.get(kSCosEq)), c_u, R(s.get(kSSinEq)) * sin_d));
   const R half_gam = R(0.5) * gam_s;
   const R K_dif = half_gam * K_h;                            // :667
-  const R K_glob = (tau * K_h) + K_dif;                      // :634, :683
+  const R K_glob = fmadd(tau, K_h, K_dif);                   // :634, :683
   const R K_bs = (half_gam * albedo) * K_glob;               // :711
-  return ((tau * K_s) + K_dif) + K_bs;                       // :909
+  return fmadd(tau, K_s, K_dif) + K_bs;                      // :909
 }
 
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
@@ -227,10 +230,10 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   }
   if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
     const R da(s.get(kSDa));
-    s.set(kSVolP, (R(s.get(kSVolP)) + ((Pp * da) * dt)).v);
+    s.set(kSVolP, fmadd(Pp * da, dt, R(s.get(kSVolP))).v);
     s.set(kSPmax, nmax(R(s.get(kSPmax)), Pp).v);
-    s.set(kSVolPR, (R(s.get(kSVolPR)) + ((P_rain * da) * dt)).v);
-    s.set(kSVolPS, (R(s.get(kSVolPS)) + ((P_snow * da) * dt)).v);
+    s.set(kSVolPR, fmadd(P_rain * da, dt, R(s.get(kSVolPR))).v);
+    s.set(kSVolPS, fmadd(P_snow * da, dt, R(s.get(kSVolPS))).v);
   }
   R p0, e_sat_air, e_air, RH, T_dew, T_surf, e_sat_surf, dT, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, rTK;
   if constexpr (P::lean) {
@@ -241,7 +244,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // Independent reciprocals / exponentials / logarithms are evaluated side by side (fm::*_n) so that their
     // dependent FP64 chains overlap.  SATTERLUND configurations never get here (the kernel runs them strictly).
     // -- three reciprocals: 1/T_K, the vapour-pressure quotient (:817), the Magnus quotient of the air (:788)
-    const double den3[3] = {T_K.v, (R(k.eps) + (R(k.one_m_eps) * q)).v, (T_air + LIT(mag_b, 237.3)).v};
+    const double den3[3] = {T_K.v, fmadd(R(k.one_m_eps), q, R(k.eps)).v, (T_air + LIT(mag_b, 237.3)).v};
     double rc3[3];
     fm::rcp3_n<3>(den3, rc3);
     rTK = R(rc3[0]);
@@ -266,9 +269,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     R bot = (uz * uz) * T_K;
     bot = sel(bot == 0.0, LIT(c001, 0.01), bot);
     const bool stable = top > 0.0;
-    const R ten_top = R(10.0) * top;
-    const R num = sel(stable, bot, bot - ten_top);
-    const R den = sel(stable, bot + ten_top, bot);
+    const R num = sel(stable, bot, fnmadd(R(10.0), top, bot));
+    const R den = sel(stable, fmadd(R(10.0), top, bot), bot);
     const R uk2 = uz * R(k.kappa2);
     const R LL = L * L;
     // -- two reciprocals: the Magnus quotient of the surface, the aerodynamic quotient
@@ -284,7 +286,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
     Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
     e_surf = RH * e_sat_surf;                                                                // :853
-    Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) * inv_p0);                  // :931-934
+    Qe = ((R(k.rho_lv_air) * Dh) * fnmadd(RH, e_sat_surf, e_air)) * (R(k.lhc) * inv_p0);     // :931-934
     // only read when a caller records them (dead code otherwise)
     p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
     e_sat_air = LIT(esat10, 6.11) / en;
@@ -343,7 +345,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     n = sel(tot < thr, n + R(k.days_per_dt), R(0.0));       // tot is finite on the sane path
   }
   R albedo(st.albedo);
-  if (h_snow > 0.0) albedo = LIT(alb_0, 0.4) + (LIT(alb_k, 0.44) * nexp((-n) * r));  // :1042-1048
+  if (h_snow > 0.0) albedo = fmadd(LIT(alb_k, 0.44), nexp((-n) * r), LIT(alb_0, 0.4));  // :1042-1048
   if (h_snow == 0.0 && h_ice > 0.0) albedo = LIT(alb_ice, 0.3);         // :1049-1053
   if (h_snow == 0.0 && h_ice == 0.0) albedo = LIT(alb_bare, 0.15);       // :1054-1058
   // ---- update_net_shortwave_radiation :1122-1139
@@ -357,7 +359,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     R term1;
     if constexpr (P::lean) term1 = R(k.emis_a) * R(fm::root7(x.v));   // x > 0 on the sane path
     else term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
-    em_air = (term1 * R(k.emis_b)) + R(k.canopy);
+    em_air = fmadd(term1, R(k.emis_b), R(k.canopy));
   } else {
     em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, divk(T_K, 2016.0))));
   }
@@ -365,7 +367,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R T_surf_K = T_surf + LIT(kelvin, 273.15);
   const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);
   R LW_out = R(k.es_sigma) * npow4(T_surf_K);
-  LW_out = LW_out + (R(k.one_m_es) * LW_in);
+  LW_out = fmadd(R(k.one_m_es), LW_in, LW_out);
   const R Qn_LW = LW_in - LW_out;
   // ---- update_net_energy_flux :1314  (Qa = Qc = 0, :312-313)
   R Q_sum = ((Qn_SW + Qn_LW) + Qh) + Qe;
@@ -378,7 +380,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if constexpr (P::strict) SM = zdiv(zdiv(relu(E_in - Eccs), dt), R(k.rho_lf));
   else SM = (relu(E_in - Eccs) * R(k.inv_dt)) * R(k.inv_rho_lf);   // a product of non-negative factors
   if constexpr (P::strict) SM = relu(SM);
-  if constexpr (VOL) s.set(kSVolSM, (R(s.get(kSVolSM)) + (((SM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1486-1487
+  if constexpr (VOL) s.set(kSVolSM, fmadd((SM * R(s.get(kSDa))) * dt, LIT(c3600, 3600.0), R(s.get(kSVolSM))).v);  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
   h_swe = xadd(h_swe, xmul(P_snow, dt));
@@ -401,7 +403,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
                      LIT(st_f, 4.86035);
     }
     const R del_T = R(k.T0) - T_wb;
-    Eccs = relu((Eccs + ((R(k.rho_cp_snow) * new_h_snow) * del_T)) - E_in);
+    Eccs = relu(fmadd(R(k.rho_cp_snow) * new_h_snow, del_T, Eccs) - E_in);
   }
   // ---- update_ice_meltrate :1418-1428 (uses the NEW h_swe and the OLD h_ice)
   R IM;
@@ -412,13 +414,15 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   Ecci = sel(h_ice == 0.0, R(0.0), Ecci);
   // ---- enforce_max_ice_meltrate :1473-1480
   if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = nmin(IM, h_iwe * R(k.inv_dt));
-  if constexpr (VOL) s.set(kSVolIM, (R(s.get(kSVolIM)) + (((IM * R(s.get(kSDa))) * dt) * 3600.0)).v);  // :1493-1494
+  if constexpr (VOL) s.set(kSVolIM, fmadd((IM * R(s.get(kSDa))) * dt, LIT(c3600, 3600.0), R(s.get(kSVolIM))).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
   IM = div3600(nmin(xmul(IM, k3600), h_iwe));
   h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
   h_iwe = relu(h_iwe);
   // ---- update_combined_meltrate :1441-1445
-  const R M_total = (IM + SM) + divk(P_rain, 3600.0);
+  R M_total;
+  if constexpr (P::strict) M_total = (IM + SM) + divk(P_rain, 3600.0);
+  else M_total = fmadd(P_rain, R(1.0 / 3600.0), IM + SM);
   // ---- update_snow_depth :1711, update_ice_depth :1726
   h_snow = xmul(h_swe, R(k.ws_ratio));
   h_ice = xmul(h_iwe, R(k.wi_ratio));
