@@ -144,6 +144,11 @@ TFG_API size_t tfg_elem_size(const tfg_ctx* ctx);
 TFG_API int tfg_set_constants(tfg_ctx* ctx, const tfg_constants* c);
 TFG_API int tfg_bind_static(tfg_ctx* ctx, int64_t n_cells, const tfg_statics* s);
 TFG_API int tfg_bind_state(tfg_ctx* ctx, const tfg_state* s);
+/* Optional forcing map: cell i reads column forcing_col[i] (dev int32 [n_cells], values in [0, n_cols)) of forcing
+ * blocks that are then [n_steps][5][n_cols] -- the cells of one catchment share the catchment's forcing series, as the
+ * reference's one-CSV-per-catchment drivers do (examples/run_topoflow_glacier.py:30-49), without replicating it per
+ * cell on the host or over PCIe.  NULL restores the default, one column per cell.  Call after tfg_bind_static.    */
+TFG_API int tfg_bind_forcing_map(tfg_ctx* ctx, const int32_t* forcing_col, int64_t n_cols);
 /* host tables for steps [0, n_steps): rows[n_steps], gmt_offset_hours[n_steps][n_tz]; copied by the library
  * (each launch carries its <= 128 rows in the kernel parameter block); replaces solar.gmt_offset_hours,
  * solar_funcs.py:1616-1637, evaluated on the host                                                 */
@@ -154,7 +159,7 @@ TFG_API int tfg_bind_time(tfg_ctx* ctx, const tfg_time_row* rows, const double* 
 /* Replaces `for _ in range(n_steps): update()` (bmi_topoflow_glacier.py:413-465, :489-490):
  * advances every cell n_steps timesteps starting at absolute step `step0` (0 = first update after
  * initialize) in ONE launch, state held in registers across steps.
- *   forcing      dev [n_steps][5][n_cells] (TFG_N_FORCING order)
+ *   forcing      dev [n_steps][5][n_cells] (TFG_N_FORCING order); [n_steps][5][n_cols] with a forcing map
  *   record       dev [n_steps][popcount(record_mask)][n_cells] or NULL: per-step series of the
  *                quantities whose tfg_rec bit is set, rows in ascending bit order
  *   basin_agg    dev [n_steps][n_basin][TFG_N_AGG] float64 or NULL: ACCUMULATED INTO (zero it first);

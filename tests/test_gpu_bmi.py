@@ -278,6 +278,51 @@ def test_long_run_is_split_into_launches_transparently(exact, cuda_device):
     assert float(whole[2][:, :, 1].abs().sum()) > 0
 
 
+@pytest.mark.parametrize("mode", ["f64", "f64_fast", "f32"])
+def test_forcing_map_equals_replicated_forcing(mode, cuda_device):
+    """tfg_bind_forcing_map: cells that share a catchment's forcing column == the same forcing replicated per cell,
+    bit for bit, through the fused run, the per-step path and the host streamer."""
+    import torch
+
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.forcing import ForcingStreamer
+    import bench
+
+    N, M, T = 700, 9, 40
+    statics, _ = bench.synthetic_host_sample(N, 1, seed=3)
+    _, fcols = bench.synthetic_host_sample(M, T, seed=4)           # [T, 5, M]: one series per catchment
+    rng = np.random.default_rng(0)
+    col = rng.integers(0, M, N).astype(np.int32)
+    col[100:400] = 3                                               # a long run of cells in one catchment
+    kw = dict(zones=[-8.0], mode=mode, horizon_steps=T + 1)
+    a = MeltEngine(statics, default_constants(), "2013040100", **kw)
+    b = MeltEngine(statics, default_constants(), "2013040100", forcing_index=col, n_forcing_cols=M, **kw)
+    c = MeltEngine(statics, default_constants(), "2013040100", forcing_index=col, n_forcing_cols=M, **kw)
+    f_cols = torch.as_tensor(fcols).to(cuda_device, a.dtype).contiguous()
+    f_full = f_cols[:, :, torch.as_tensor(col, dtype=torch.int64, device=cuda_device)].contiguous()
+    a.run(f_full)
+    b.run(f_cols)
+    # host streamer on [T, 6, M] raw columns, then per-step update() from the [7, M] input block
+    raw = np.stack([fcols[:, 0] * 1e3, fcols[:, 1] + 273.15, fcols[:, 2], fcols[:, 3], fcols[:, 4], np.zeros_like(fcols[:, 4])], axis=1)
+    d = MeltEngine(statics, default_constants(), "2013040100", forcing_index=col, n_forcing_cols=M, **kw)
+    ForcingStreamer(d, chunk_steps=7, raw_dtype="float64").drive(np.ascontiguousarray(raw))
+    ref = MeltEngine(statics, default_constants(), "2013040100", forcing_index=col, n_forcing_cols=M, **kw)
+    from topoflow_glacier_b200.forcing import convert_on_host
+    ref.run(torch.as_tensor(convert_on_host(raw)).to(cuda_device, a.dtype).contiguous())
+    for t in range(T):
+        c.inputs[:5].copy_(f_cols[t])
+        c.step()
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state) and torch.equal(a.ring, b.ring)
+    assert torch.equal(a.state, c.state) and torch.equal(a.ring, c.ring)
+    assert torch.equal(d.state, ref.state)
+    with pytest.raises(ValueError):
+        b.run(f_full)                                              # a per-cell block no longer fits the map
+    for e in (a, b, c, d, ref):
+        e.close()
+
+
 def test_checkpoint_resume_is_bit_identical(tmp_path, cuda_device):
     """state + snowfall window + step counter saved mid-run, resumed in a fresh model == uninterrupted run."""
     import torch

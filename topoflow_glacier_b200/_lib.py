@@ -68,6 +68,7 @@ PROTOTYPES = {
     "tfg_set_constants": (C.c_int, [C.c_void_p, C.POINTER(Constants)]),
     "tfg_bind_static": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Statics)]),
     "tfg_bind_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
+    "tfg_bind_forcing_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "tfg_bind_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "tfg_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                           C.c_int32, C.c_void_p]),

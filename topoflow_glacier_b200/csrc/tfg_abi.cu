@@ -46,6 +46,8 @@ struct tfg_ctx {
   int n_tz = 1;
   int use_tma = 0;  // forcing tiles staged by the TMA copy engine (tfg_set_option)
   int64_t exact_agg = 0;  // TFG_OPT_EXACT_AGG value (0 = floating-point atomics)
+  const int32_t* forcing_col = nullptr;  // tfg_bind_forcing_map
+  int64_t n_cols = 0;
 };
 
 namespace {
@@ -114,6 +116,8 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
   p.exact_ring = (n_steps == 1);
   p.use_tma = x->use_tma;
   p.forcing = static_cast<const raw*>(forcing);
+  p.forcing_col = x->forcing_col;
+  p.n_cols = x->forcing_col ? x->n_cols : x->n_cells;
 #define S(f) p.f = static_cast<const raw*>(x->s.f)
   S(a_elev); S(sin_lat); S(cos_lat); S(neg_tan_lat); S(lon); S(dlon); S(t_noon); S(da_m2);
 #undef S
@@ -311,6 +315,14 @@ int tfg_bind_static(tfg_ctx* x, int64_t n_cells, const tfg_statics* s) {
   return 0;
 }
 
+int tfg_bind_forcing_map(tfg_ctx* x, const int32_t* forcing_col, int64_t n_cols) {
+  if (!x) return fail("tfg_bind_forcing_map: NULL context");
+  if (forcing_col && n_cols <= 0) return fail("tfg_bind_forcing_map: n_cols must be > 0");
+  x->forcing_col = forcing_col;
+  x->n_cols = forcing_col ? n_cols : 0;
+  return 0;
+}
+
 int tfg_bind_state(tfg_ctx* x, const tfg_state* s) {
   if (!x || !s) return fail("tfg_bind_state: NULL argument");
   void* req[] = {s->h_snow, s->h_swe, s->h_ice, s->h_iwe, s->eccs, s->ecci, s->albedo, s->n_days,
@@ -355,7 +367,7 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
   // (bit-identical to one launch: state and snowfall window are carried through HBM either way)
   for (int32_t t0 = 0; t0 < n_steps && e == cudaSuccess; t0 += tfg::kMaxLaunchSteps) {
     const int32_t nt = std::min<int32_t>(tfg::kMaxLaunchSteps, n_steps - t0);
-    const void* f = static_cast<const char*>(forcing) + (size_t)t0 * TFG_N_FORCING * x->n_cells * es;
+    const void* f = static_cast<const char*>(forcing) + (size_t)t0 * TFG_N_FORCING * (x->forcing_col ? x->n_cols : x->n_cells) * es;
     void* r = record ? static_cast<char*>(record) + (size_t)t0 * __builtin_popcountll(record_mask) * x->n_cells * es : nullptr;
     // float64 sums: 8 B per entry; exact mode: two int64 words per entry (the trailing counter stays at the end)
     void* a = basin_agg ? static_cast<char*>(basin_agg) + (size_t)t0 * n_basin * TFG_N_AGG * (x->exact_agg ? 16 : 8) : nullptr;

@@ -37,6 +37,8 @@ struct RunParams {
   int64_t n_cells, step0;
   int32_t n_steps, ring_slots, n_tz, exact_ring, use_tma;
   const raw* forcing;
+  const int32_t* forcing_col;  // optional: cell -> column of the forcing block (cells of one catchment share a column)
+  int64_t n_cols;              // columns of the forcing block (= n_cells without a map)
   const raw *a_elev, *sin_lat, *cos_lat, *neg_tan_lat, *lon, *sin_eq, *cos_eq, *neg_tan_eq, *dlon, *t_noon, *da_m2,
       *t_rs;
   const int32_t* basin_id;
@@ -204,7 +206,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     warp_uniform = __all_sync(0xffffffffu, basin == __shfl_sync(0xffffffffu, basin, 0));
   }
 
-  const raw* f = p.forcing + c;
+  // forcing block [step][var][column]: column = cell, or the cell's entry of the forcing map
+  const int64_t FN = p.n_cols;
+  const raw* f = p.forcing + (p.forcing_col ? (int64_t)__ldg(p.forcing_col + c) : c);
   raw f0, f1, f2, f3, f4;
   __shared__ alignas(128) raw sm_force[TMA ? kStages : 1][TFG_N_FORCING][TMA ? kBlock : 1];
   __shared__ uint64_t bar_full[kStages], bar_empty[kStages];
@@ -214,9 +218,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   constexpr bool kCp = TFG_CPASYNC && !TMA;
   __shared__ raw sm_next[kCp ? 2 : 1][TFG_N_FORCING][kCp ? kBlock : 1];
   auto stage_forcing = [&](int step_t) {
-    const raw* fn = f + (int64_t)step_t * (TFG_N_FORCING * N);
+    const raw* fn = f + (int64_t)step_t * (TFG_N_FORCING * FN);
 #pragma unroll
-    for (int v = 0; v < TFG_N_FORCING; ++v) cp_async_elem(&sm_next[step_t & 1][v][threadIdx.x], fn + (int64_t)v * N);
+    for (int v = 0; v < TFG_N_FORCING; ++v) cp_async_elem(&sm_next[step_t & 1][v][threadIdx.x], fn + (int64_t)v * FN);
     cp_async_commit();
   };
   auto issue_stage = [&](int step_t) {  // elected thread: five row copies for timestep step_t
@@ -238,8 +242,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   } else if constexpr (kCp) {
     stage_forcing(0);
   } else {
-    f0 = ld_stream(f); f1 = ld_stream(f + N); f2 = ld_stream(f + 2 * N); f3 = ld_stream(f + 3 * N);
-    f4 = ld_stream(f + 4 * N);
+    f0 = ld_stream(f); f1 = ld_stream(f + FN); f2 = ld_stream(f + 2 * FN); f3 = ld_stream(f + 3 * FN);
+    f4 = ld_stream(f + 4 * FN);
   }
   // float32 kernel: the slot pointer walks through the window (no 64-bit multiply per step); the float64 kernels
   // are register-bound and recompute the address instead of carrying two more pointers
@@ -335,9 +339,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       if constexpr (!TMA && !kCp) {
         g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
         if (t + 1 < p.n_steps) {
-          const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * N);
-          g0 = ld_stream(fn); g1 = ld_stream(fn + N); g2 = ld_stream(fn + 2 * N); g3 = ld_stream(fn + 3 * N);
-          g4 = ld_stream(fn + 4 * N);
+          const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * FN);
+          g0 = ld_stream(fn); g1 = ld_stream(fn + FN); g2 = ld_stream(fn + 2 * FN); g3 = ld_stream(fn + 3 * FN);
+          g4 = ld_stream(fn + 4 * FN);
         }
       }
     };
@@ -455,7 +459,7 @@ template <class P>
 cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, bool vol, cudaStream_t stream) {
   const unsigned grid = (unsigned)((p.n_cells + kBlock - 1) / kBlock);
   // TMA staging needs whole blocks and 16-byte aligned rows; otherwise the register-prefetch kernel runs
-  const bool tma = p.use_tma && !rec && (p.n_cells % kBlock == 0) && p.n_steps >= 2 &&
+  const bool tma = p.use_tma && !rec && !p.forcing_col && (p.n_cells % kBlock == 0) && p.n_steps >= 2 &&
                    ((reinterpret_cast<uintptr_t>(p.forcing) & 15) == 0) &&
                    ((p.n_cells * sizeof(typename P::raw)) % 16 == 0);
   const size_t dyn = P::lean ? fm::kTabDoubles * sizeof(double) : 0;

@@ -48,6 +48,9 @@ class MeltEngine:
     consts : mapping holding the physical constants (``config.KERNEL_CONSTANTS`` keys, ``SATTERLUND``)
     start_time : ``YYYYMMDDHH`` string; ``dt_hours`` : timestep [h]
     zones : list of IANA names / fixed offsets; ``tz_idx`` : per-cell index into it (uint8) or None
+    forcing_index : optional per-cell int32 column of the forcing blocks (``n_forcing_cols`` columns): the cells of
+        one catchment share the catchment's forcing series, so forcing is ``[T, 5, n_forcing_cols]`` instead of
+        ``[T, 5, N]`` -- nothing is replicated per cell on the host or over PCIe (``tfg_bind_forcing_map``)
     basin_id : per-cell int32 basin index in ``[0, n_basin)`` or None
     mode : ``"f64"`` (strict), ``"f64_fast"`` or ``"f32"``
     horizon_steps : number of steps the host time tables are prepared for (extended on demand)
@@ -57,7 +60,7 @@ class MeltEngine:
                  zones: Sequence = ("America/Los_Angeles",), tz_idx: Optional[np.ndarray] = None,
                  basin_id: Optional[np.ndarray] = None, n_basin: int = 0, mode: str = "f64", device: int = 0,
                  horizon_steps: int = 24 * 366, diag_integrals: bool = True, device_statics: Optional[dict] = None,
-                 tma_staging: Optional[bool] = None):
+                 tma_staging: Optional[bool] = None, forcing_index=None, n_forcing_cols: Optional[int] = None):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.mode = _lib.MODE_NAMES[mode] if isinstance(mode, str) else int(mode)
@@ -108,8 +111,19 @@ class MeltEngine:
             self.tz_idx = None if tz_idx is None else torch.as_tensor(
                 np.ascontiguousarray(tz_idx, dtype=np.uint8)).to(self.device)
             self._bind_static()
+            self.n_cols, self.forcing_index = N, None
+            if forcing_index is not None:
+                fi = forcing_index if torch.is_tensor(forcing_index) else torch.as_tensor(np.ascontiguousarray(forcing_index))
+                fi = fi.to(self.device, torch.int32).contiguous()
+                if fi.numel() != N:
+                    raise ValueError("forcing_index must have one entry per cell")
+                self.n_cols = int(n_forcing_cols) if n_forcing_cols is not None else int(fi.max().item()) + 1
+                if int(fi.min().item()) < 0 or int(fi.max().item()) >= self.n_cols:
+                    raise ValueError("forcing_index entries must lie in [0, n_forcing_cols)")
+                self.forcing_index = fi
+                _lib.check(self.lib.tfg_bind_forcing_map(self.ctx, fi.data_ptr(), self.n_cols), "tfg_bind_forcing_map")
 
-            self.inputs = torch.zeros(len(INPUT_ROWS), N, dtype=self.dtype, device=self.device)
+            self.inputs = torch.zeros(len(INPUT_ROWS), self.n_cols, dtype=self.dtype, device=self.device)
             self.state = torch.zeros(len(STATE_ROWS), N, dtype=self.dtype, device=self.device)
             self.ring = torch.zeros(self.ring_slots, N, dtype=self.dtype, device=self.device)
             self.diag_integrals = diag_integrals
@@ -200,8 +214,10 @@ class MeltEngine:
         T = int(n_steps if n_steps is not None else forcing.shape[0])
         if forcing.dtype != self.dtype or not forcing.is_cuda or not forcing.is_contiguous():
             raise ValueError("forcing must be a contiguous device tensor of the engine dtype")
-        if forcing.numel() < T * _lib.N_FORCING * self.N:
-            raise ValueError("forcing block smaller than [n_steps, 5, N]")
+        if forcing.numel() < T * _lib.N_FORCING * self.n_cols:
+            raise ValueError("forcing block smaller than [n_steps, 5, N]  (N = n_forcing_cols with a forcing map)")
+        if self.forcing_index is not None and forcing.dim() == 3 and forcing.shape[2] != self.n_cols:
+            raise ValueError(f"forcing must have {self.n_cols} columns (forcing map)")
         self.ensure_horizon(self.step_index + T)
         rec_t, mask, names = None, 0, []
         if record:
@@ -252,7 +268,7 @@ class MeltEngine:
 
     def synth_forcing(self, out: torch.Tensor, step0: int, n_steps: int, elev: torch.Tensor, seed: int,
                       storm_cells: int = 1):
-        _lib.check(self.lib.tfg_synth_forcing(self.ctx, out.data_ptr(), step0, n_steps, self.N, elev.data_ptr(), seed,
+        _lib.check(self.lib.tfg_synth_forcing(self.ctx, out.data_ptr(), step0, n_steps, int(out.shape[-1]), elev.data_ptr(), seed,
                                               int(storm_cells), self.stream_ptr), "tfg_synth_forcing")
 
     # ---- hydrograph routing stand-in --------------------------------------------------

@@ -75,7 +75,8 @@ class ForcingStreamer:
         self.e = engine
         self.Tc = int(chunk_steps)
         self.nb = int(n_buffers)
-        N, dev = engine.N, engine.device
+        N, dev = engine.n_cols, engine.device   # forcing columns (= cells unless the engine has a forcing map)
+        self.N = N
         self.side = torch.cuda.Stream(device=dev)
         self.raw_dtype = torch.float32 if str(raw_dtype).endswith("32") else torch.float64
         self.raw_es = 4 if self.raw_dtype == torch.float32 else 8
@@ -100,17 +101,17 @@ class ForcingStreamer:
             self._keepalive = block
         else:
             if self.pinned[b] is None:
-                self.pinned[b] = torch.empty(self.Tc, 6, e.N, dtype=self.raw_dtype).pin_memory()
+                self.pinned[b] = torch.empty(self.Tc, 6, self.N, dtype=self.raw_dtype).pin_memory()
             self.h2d_done[b].synchronize()  # pinned buffer free again
             self.pinned[b][:Tk].numpy()[...] = block.numpy() if torch.is_tensor(block) else block
             src_ptr = self.pinned[b].data_ptr()
         self.side.wait_event(self.consumed[b])  # device buffers free again
-        nbytes = Tk * 6 * e.N * self.raw_es
+        nbytes = Tk * 6 * self.N * self.raw_es
         with torch.cuda.device(e.device):
             self._lib.check(lib.tfg_ingest_async(e.ctx, src_ptr, self.d_raw[b].data_ptr(), nbytes,
                                                  self.side.cuda_stream, None), "tfg_ingest_async")
             self.h2d_done[b].record(self.side)
-            self._lib.check(lib.tfg_convert_forcing(e.ctx, self.d_raw[b].data_ptr(), self.raw_es, self.d_out[b].data_ptr(), Tk, e.N,
+            self._lib.check(lib.tfg_convert_forcing(e.ctx, self.d_raw[b].data_ptr(), self.raw_es, self.d_out[b].data_ptr(), Tk, self.N,
                                                     self.side.cuda_stream), "tfg_convert_forcing")
             self.ready[b].record(self.side)
         self.h2d_bytes += nbytes
