@@ -113,15 +113,7 @@ class MeltEngine:
             self._bind_static()
             self.n_cols, self.forcing_index = N, None
             if forcing_index is not None:
-                fi = forcing_index if torch.is_tensor(forcing_index) else torch.as_tensor(np.ascontiguousarray(forcing_index))
-                fi = fi.to(self.device, torch.int32).contiguous()
-                if fi.numel() != N:
-                    raise ValueError("forcing_index must have one entry per cell")
-                self.n_cols = int(n_forcing_cols) if n_forcing_cols is not None else int(fi.max().item()) + 1
-                if int(fi.min().item()) < 0 or int(fi.max().item()) >= self.n_cols:
-                    raise ValueError("forcing_index entries must lie in [0, n_forcing_cols)")
-                self.forcing_index = fi
-                _lib.check(self.lib.tfg_bind_forcing_map(self.ctx, fi.data_ptr(), self.n_cols), "tfg_bind_forcing_map")
+                self.set_forcing_map(forcing_index, n_forcing_cols, _alloc_inputs=False)
 
             self.inputs = torch.zeros(len(INPUT_ROWS), self.n_cols, dtype=self.dtype, device=self.device)
             self.state = torch.zeros(len(STATE_ROWS), N, dtype=self.dtype, device=self.device)
@@ -245,6 +237,26 @@ class MeltEngine:
                 "tfg_run")
         self.step_index += T
         return {k: rec_t[:, i] for i, k in enumerate(names)} if rec_t is not None else {}
+
+    def set_forcing_map(self, forcing_index, n_forcing_cols: Optional[int] = None, _alloc_inputs: bool = True):
+        """(Re)bind the cell -> forcing-column map (``None`` restores one column per cell); the input block of the
+        per-step path is re-allocated with one column per forcing column."""
+        if forcing_index is None:
+            self.n_cols, self.forcing_index = self.N, None
+            _lib.check(self.lib.tfg_bind_forcing_map(self.ctx, None, 0), "tfg_bind_forcing_map")
+        else:
+            fi = forcing_index if torch.is_tensor(forcing_index) else torch.as_tensor(np.ascontiguousarray(forcing_index))
+            fi = fi.to(self.device, torch.int32).contiguous()
+            if fi.numel() != self.N:
+                raise ValueError("forcing_index must have one entry per cell")
+            n_cols = int(n_forcing_cols) if n_forcing_cols is not None else int(fi.max().item()) + 1
+            if int(fi.min().item()) < 0 or int(fi.max().item()) >= n_cols:
+                raise ValueError("forcing_index entries must lie in [0, n_forcing_cols)")
+            self.n_cols, self.forcing_index = n_cols, fi
+            _lib.check(self.lib.tfg_bind_forcing_map(self.ctx, fi.data_ptr(), n_cols), "tfg_bind_forcing_map")
+        if _alloc_inputs:
+            torch.cuda.synchronize(self.device)
+            self.inputs = torch.zeros(len(INPUT_ROWS), self.n_cols, dtype=self.dtype, device=self.device)
 
     # ---- order-independent basin aggregates (TFG_OPT_EXACT_AGG, include/tfglacier.h) ---------------------------
     def agg_exponents(self):
