@@ -1,0 +1,36 @@
+"""bench.py contract, CPU side: the reference arm prints ONE JSON line with the keys the driver reads."""
+
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-cells", "4096", "--cpu-steps", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "cell_timesteps_per_sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_gpu_arm_refuses_to_run_without_cuda():
+    """The product path has no CPU fallback: without a CUDA device the GPU arm must fail loudly."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--no-cpu", "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert r.returncode != 0
+    assert "CUDA" in (r.stderr + r.stdout)
