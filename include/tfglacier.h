@@ -144,6 +144,12 @@ TFG_API size_t tfg_elem_size(const tfg_ctx* ctx);
 TFG_API int tfg_set_constants(tfg_ctx* ctx, const tfg_constants* c);
 TFG_API int tfg_bind_static(tfg_ctx* ctx, int64_t n_cells, const tfg_statics* s);
 TFG_API int tfg_bind_state(tfg_ctx* ctx, const tfg_state* s);
+/* Optional [3][n_cells] scratch (context element type, initialise the third row to NaN): the kernel keeps the running
+ * sum of the 3-day snowfall window there between launches, so that a launch of a few timesteps does not re-read all
+ * ring_slots entries of every cell; an exact re-sum still happens whenever the sum is within rounding distance of the
+ * 0.03 m threshold (bmi_topoflow_glacier.py:1040), so decisions -- and hence all state -- are unchanged.  Set the third
+ * row to NaN after changing the window from outside.  NULL switches it off.                                        */
+TFG_API int tfg_bind_window_carry(tfg_ctx* ctx, void* carry);
 /* Optional forcing map: cell i reads column forcing_col[i] (dev int32 [n_cells], values in [0, n_cols)) of forcing
  * blocks that are then [n_steps][5][n_cols] -- the cells of one catchment share the catchment's forcing series, as the
  * reference's one-CSV-per-catchment drivers do (examples/run_topoflow_glacier.py:30-49), without replicating it per

@@ -259,8 +259,9 @@ def test_time_zones_and_dst_per_cell(mode, cuda_device):
         assert ok, (k, ratio, dabs, drel)
 
 
+@pytest.mark.parametrize("chunk", [0, 7])
 @pytest.mark.parametrize("mode", ["f64", "f64_fast"])
-def test_snowfall_window_threshold_knife_edge(mode, cuda_device):
+def test_snowfall_window_threshold_knife_edge(mode, chunk, cuda_device):
     """The 3-day snowfall total is steered to within ~1e-13 of the 0.03 m threshold (:1040).  The fused kernel keeps
     an incremental sum and must fall back to the exact reference-order re-sum inside its guard band, so the
     'days since snowfall' counter n must equal the oracle's at every step, exactly."""
@@ -278,7 +279,16 @@ def test_snowfall_window_threshold_knife_edge(mode, cuda_device):
     ora = make_oracle(c2, strict_pow=True)
     want = ora.run(forcing, record=("n", "snow3day", "albedo"))
     eng = make_engine(c2, mode=mode)
-    got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).cuda(), record=("n", "snow3day", "albedo")).items()}
+    f_dev = torch.as_tensor(forcing).cuda()
+    if chunk:   # short launches: the running window sum is carried from launch to launch (tfg_bind_window_carry)
+        parts = []
+        for t0 in range(0, T, chunk):
+            parts.append(eng.run(f_dev[t0:t0 + chunk].contiguous(), record=("n", "snow3day", "albedo")))
+            if t0 == chunk:
+                assert torch.isfinite(eng.window_carry[2]).all()    # ... and is in use
+        got = {k: torch.cat([pp[k] for pp in parts]).cpu().numpy() for k in parts[0]}
+    else:
+        got = {k: v.cpu().numpy() for k, v in eng.run(f_dev, record=("n", "snow3day", "albedo")).items()}
     eng.close()
     near = np.abs(want["snow3day"] - 0.03) < 1e-12
     assert near.sum() > 100, near.sum()                     # the test really sits on the knife edge

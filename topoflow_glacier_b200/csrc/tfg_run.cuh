@@ -46,6 +46,8 @@ struct RunParams {
   raw *h_snow, *h_swe, *h_ice, *h_iwe, *eccs, *ecci, *albedo, *n_days, *SM, *IM, *M_total, *RH;
   raw *vol_P, *vol_PR, *vol_PS, *vol_SM, *vol_IM, *P_max;
   raw* ring;
+  raw* win_carry;  // optional [3][n_cells]: incremental window sum, its largest magnitude and its rounding count, carried
+                   // from launch to launch so that short launches need not re-read all 72 slots (NaN count = re-seed)
   // Clock-only tables of THIS launch, passed in the kernel parameter block (constant bank): the step index is
   // warp-uniform, so a row is read with uniform loads straight into the operand slots of the FP64 instructions
   // instead of occupying 16 vector registers per thread for the whole step.
@@ -190,13 +192,24 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   const bool exact = p.exact_ring != 0;
   // incremental window sum: seeded from the stored window, re-derived exactly (reference summation
   // order) whenever it comes within a guard band of the 0.03 m threshold of :1040
-  R tot(0.0);
-  if (!exact) {
-    for (int j = 0; j < slots; ++j) tot = xadd(tot, R(ring[(int64_t)j * N]));
-  }
-  R tot_hi = nabs(tot);
+  R tot(0.0), tot_hi(0.0);
   const R guard(P::f32 ? 1.2e-7 : 2.3e-16);  // two units of round-off per counted operation
   R n_round((double)slots + 16.0);  // seeding additions + the reference sum's own depth
+  // The fast mode's fixed band (below) covers 600 roundings of sums up to 1e4 m; the scaled bands of the other modes
+  // stay narrow up to a few hundred.  A carried sum is used while this launch keeps the count below that.
+  constexpr double kMaxRoundings = P::lean ? 600.0 : 400.0;
+  bool carried = false;
+  if (!exact && p.win_carry != nullptr) {
+    const R n0(p.win_carry[2 * N + c]);
+    if (n0.v + (raw)(2 * p.n_steps) <= (raw)kMaxRoundings) {  // false for the NaN that marks "no valid sum"
+      tot = R(p.win_carry[c]); tot_hi = R(p.win_carry[N + c]); n_round = n0;
+      carried = true;
+    }
+  }
+  if (!exact && !carried) {
+    for (int j = 0; j < slots; ++j) tot = xadd(tot, R(ring[(int64_t)j * N]));
+    tot_hi = nabs(tot);
+  }
 
   int basin = 0;
   bool warp_uniform = false;
@@ -443,6 +456,14 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     if constexpr (kWalk) ring_cur = ring_next;
   }
 
+  if (active && p.win_carry != nullptr) {
+    if (exact) {
+      p.win_carry[2 * N + c] = (raw)nan("");  // the window moved without the running sum: re-seed next time
+    } else {
+      if constexpr (P::lean) n_round = n_round + R((double)(2 * p.n_steps));  // not counted per step in this mode
+      p.win_carry[c] = tot.v; p.win_carry[N + c] = nmax(tot_hi, nabs(tot)).v; p.win_carry[2 * N + c] = n_round.v;
+    }
+  }
   if (active) {
     p.h_snow[c] = st.h_snow; p.h_swe[c] = st.h_swe; p.h_ice[c] = st.h_ice; p.h_iwe[c] = st.h_iwe;
     p.eccs[c] = st.eccs; p.ecci[c] = st.ecci; p.albedo[c] = st.albedo; p.n_days[c] = st.n_days;

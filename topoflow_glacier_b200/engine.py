@@ -168,6 +168,13 @@ class MeltEngine:
             setattr(s, _STATE_FIELD[name], ptr)
         s.ring = self.ring.data_ptr()
         _lib.check(self.lib.tfg_bind_state(self.ctx, C.byref(s)), "tfg_bind_state")
+        # running sum of the snowfall window carried between launches (tfg_bind_window_carry); NaN count = re-seed
+        self.window_carry = torch.full((3, self.N), float("nan"), dtype=self.dtype, device=self.device)
+        _lib.check(self.lib.tfg_bind_window_carry(self.ctx, self.window_carry.data_ptr()), "tfg_bind_window_carry")
+
+    def invalidate_window_sum(self):
+        """Call after writing to ``ring`` from outside the kernels: the next launch re-sums the window."""
+        self.window_carry[2].fill_(float("nan"))
 
     def ensure_horizon(self, n_steps: int):
         """Make sure host time tables cover absolute steps ``[0, n_steps)``."""
@@ -313,6 +320,7 @@ class MeltEngine:
                 raise ValueError(f"checkpoint {k}={sd[k]!r} does not match this engine ({mine!r})")
         self.state.copy_(sd["state"])
         self.ring.copy_(sd["ring"])
+        self.invalidate_window_sum()
         self.inputs.copy_(sd["inputs"])
         self.step_index = int(sd["step_index"])
         self.ensure_horizon(self.step_index + 1)
