@@ -270,7 +270,15 @@ class MeltEngine:
         """Binary exponents E_q with |32-cell partial of aggregate q| < 2^E_q for physically possible values:
         M_total < 2^-8 m/s (10 m/h of rain is 2.8e-3), water-equivalent depths < 2^17 m."""
         if self._agg_exp is None:
-            da_max = float(self.static["da_m2"].max().item())
+            da_max_t = self.static["da_m2"].max().to(torch.float64)
+            try:  # every rank must scale with the SAME exponents, or the integer all-reduce adds apples and pears
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    dist.all_reduce(da_max_t, op=dist.ReduceOp.MAX)   # collective: call on all ranks
+            except ImportError:
+                pass
+            da_max = float(da_max_t.item())
             e_da = int(np.ceil(np.log2(max(da_max, 1e-30) * 32.0)))
             self._agg_exp = (e_da - 8, e_da + 17, e_da + 17)
         return self._agg_exp
