@@ -323,6 +323,31 @@ def test_forcing_map_equals_replicated_forcing(mode, cuda_device):
         e.close()
 
 
+def test_bmi_ensemble_with_shared_forcing_series(cuda_device):
+    """BMI surface on an ensemble whose members share forcing series: inputs hold one value per series."""
+    from topoflow_glacier import BmiTopoflowGlacier
+
+    z = np.load(GOLDEN / "cats288.npz")
+    keys = ("da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow")
+    cfgs = [dict({k: float(z[f"static_{k}"][i % 4]) for k in keys}, site_prefix=f"c{i}", forcing_file="-", dt=1,
+                 start_time="2013032000", end_time="2013033123") for i in range(6)]
+    col = np.array([0, 0, 1, 1, 1, 0], dtype=np.int32)
+    shared = BmiTopoflowGlacier(); shared.initialize_ensemble(cfgs, forcing_index=col, n_forcing_cols=2)
+    plain = BmiTopoflowGlacier(); plain.initialize_ensemble(cfgs)
+    f = z["forcing"][:12, :, :2]                                  # two series
+    names = ("atmosphere_water__liquid_equivalent_precipitation_rate", "land_surface_air__temperature",
+             "land_surface_air__pressure", "atmosphere_air_water~vapor__relative_saturation", "wind_speed_UV")
+    dest_s, dest_p = np.zeros(6), np.zeros(6)
+    for t in range(f.shape[0]):
+        for j, name in enumerate(names):
+            shared.set_value(name, f[t, j])                       # 2 values
+            plain.set_value(name, f[t, j][col])                   # 6 values
+        shared.update(); plain.update()
+        for name in shared.get_output_var_names():
+            assert np.array_equal(shared.get_value(name, dest_s), plain.get_value(name, dest_p)), (t, name)
+    shared.finalize(); plain.finalize()
+
+
 def test_checkpoint_resume_is_bit_identical(tmp_path, cuda_device):
     """state + snowfall window + step counter saved mid-run, resumed in a fresh model == uninterrupted run."""
     import torch

@@ -89,7 +89,11 @@ class BmiTopoflowGlacier(_BmiBase):
         self._build(cfgs)
 
     def initialize_ensemble(self, configs: Sequence, **engine_kw) -> None:
-        """Extension: N catchments (config paths, dicts or validated objects) as one device-resident model."""
+        """Extension: N catchments (config paths, dicts or validated objects) as one device-resident model.
+
+        ``engine_kw`` reaches ``MeltEngine``: e.g. ``mode="f64_fast"``, ``basin_id=..., n_basin=...`` or
+        ``forcing_index=..., n_forcing_cols=M`` (members that share a forcing series: the input variables then hold
+        ``M`` values, one per series)."""
         cfgs = []
         for c in configs:
             if isinstance(c, (str, Path)):
@@ -131,7 +135,8 @@ class BmiTopoflowGlacier(_BmiBase):
         e = self._engine
         self._n = e.N
         # pinned staging: inputs (upload at update) and outputs (download at first get after update)
-        self._in_host = torch.zeros(len(INPUT_ROWS), e.N, dtype=e.dtype).pin_memory()
+        # (one column per cell, or per forcing column when the ensemble was built with forcing_index=...)
+        self._in_host = torch.zeros(len(INPUT_ROWS), e.n_cols, dtype=e.dtype).pin_memory()
         self._in_dirty = np.zeros(len(INPUT_ROWS), dtype=bool)
         self._out_host = torch.zeros(len(_OUT_INTERNAL), e.N, dtype=e.dtype).pin_memory()
         self._out_rows = torch.tensor([self._state_row(k) for k in _OUT_INTERNAL], device=e.device)
