@@ -64,7 +64,8 @@ class BasinAggregates:
     floating-point atomics; ``reduce`` makes it global (in place) with one ``all_reduce(SUM)``.  Reproducible to
     rounding (~1e-15), not bit for bit: the order of the atomics is not fixed.
 
-    ``exponents=(E0, E1, E2)`` (``MeltEngine.agg_exponents()``) selects ORDER-INDEPENDENT sums instead: the kernel
+    ``exponents=(E0, E1, E2)`` (``MeltEngine.agg_exponents()``, which agrees them across ranks with one
+    ``all_reduce(MAX)`` -- every rank must scale with the same exponents) selects ORDER-INDEPENDENT sums instead: the kernel
     splits every contribution into two fixed-point int64 words and adds them with integer atomics
     (``TFG_OPT_EXACT_AGG``); ``accumulator`` is that int64 tensor (pass it to ``MeltEngine.run(basin_agg=...)``),
     ``reduce`` all-reduces the integers -- exactly -- and decodes them into ``buffer``.  The result is bit-identical
