@@ -64,3 +64,14 @@ def test_no_gpu_fails_loudly():
             {"site_prefix": "x", "forcing_file": "x", "dt": 1, "start_time": 2013032000, "end_time": "2013033100",
              "da": 1.0, "slope": 1.0, "lat": 46.0, "lon": -121.0, "h0_snow": 0, "h0_ice": 0, "h0_swe": 0,
              "h0_iwe": 0, "elev": 100.0})])
+
+
+def test_build_flags_that_results_depend_on():
+    """The fast float64 unit must not contract multiply-adds implicitly (bit-identical template instantiations), the
+    float32 unit is built flush-to-zero, and everything targets sm_100a."""
+    from topoflow_glacier_b200 import build
+
+    assert "arch=compute_100a,code=sm_100a" in build.NVCC_FLAGS
+    assert "-fmad=false" in build.EXTRA_FLAGS["tfg_run_fast.cu"]
+    assert "-ftz=true" in build.EXTRA_FLAGS["tfg_run_f32.cu"]
+    assert "tfg_run_strict.cu" not in build.EXTRA_FLAGS      # strict: single-rounding intrinsics, no special flags
