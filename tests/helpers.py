@@ -8,7 +8,8 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 STATIC_KEYS = ["da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow"]
-CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "satterlund", "dt2", "year4"]
+CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "satterlund", "dt2", "year4",
+         "cfgspace", "south_dt3", "polar", "dt24", "year2070"]
 
 # |gpu - ref| <= rtol*|ref| + atol, float64 modes (the atol of a flux is ~1e-12 x the size of
 # the terms that cancel in it, see DESIGN.md "Tolerances")
@@ -38,7 +39,13 @@ def load_case(name: str) -> dict:
     dt = int(consts.pop("dt", 1))
     if "SATTERLUND" in consts:
         consts["SATTERLUND"] = bool(consts["SATTERLUND"])
-    return {"name": name, "statics": statics, "N": N, "forcing": np.ascontiguousarray(forcing), "dt": dt,
+    tz = str(z["tz_name"]) if "tz_name" in z.files else "America/Los_Angeles"
+    if "generated_year" in z.files:  # vectors that depend on the year they were generated in (see make_golden.py)
+        from datetime import datetime
+
+        if int(z["generated_year"]) != datetime.now().year:
+            ref = {}
+    return {"name": name, "tz": tz, "statics": statics, "N": N, "forcing": np.ascontiguousarray(forcing), "dt": dt,
             "consts": consts, "start_time": str(z["start_time"]), "ref": ref, "rows": rows, **extra}
 
 
@@ -46,7 +53,7 @@ def make_oracle(case: dict, strict_pow: bool = False, consts: dict | None = None
     from oracle.np_ref import CellStatics, Constants, OracleModel
 
     s = case["statics"]
-    cells = CellStatics(**{k: s[k].astype(np.float64) for k in STATIC_KEYS}, tz=["America/Los_Angeles"])
+    cells = CellStatics(**{k: s[k].astype(np.float64) for k in STATIC_KEYS}, tz=[case.get("tz", "America/Los_Angeles")])
     kw = dict(case.get("consts", {}), dt=case.get("dt", 1))
     kw.update(consts or {})
     return OracleModel(cells, Constants(**kw), start_time=case["start_time"], strict_pow=strict_pow)
@@ -64,7 +71,8 @@ def make_engine(case: dict, mode: str = "f64", **kw):
     consts = default_constants()
     consts.update(case.get("consts", {}))
     consts.update(kw.pop("consts", {}))
-    return MeltEngine(case["statics"], consts, case["start_time"], dt_hours=case.get("dt", 1), zones=["America/Los_Angeles"],
+    return MeltEngine(case["statics"], consts, case["start_time"], dt_hours=case.get("dt", 1),
+                      zones=[case.get("tz", "America/Los_Angeles")],
                       mode=mode, horizon_steps=case["forcing"].shape[0] + 1, **kw)
 
 

@@ -399,3 +399,244 @@ def test_mock_routing_fir_matches_numpy_convolve(cuda_device):
         want = np.convolve(qh[:, j], w, mode="full")[: qh.shape[0]]
         np.testing.assert_allclose(routed[:, j], want, rtol=1e-13, atol=1e-18)
     eng.close()
+
+
+def _shared_ensemble(n_members=6):
+    from topoflow_glacier import BmiTopoflowGlacier
+
+    z = np.load(GOLDEN / "cats288.npz")
+    keys = ("da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow")
+    cfgs = [dict({k: float(z[f"static_{k}"][i % 4]) for k in keys}, site_prefix=f"c{i}", forcing_file="-", dt=1,
+                 start_time="2013032000", end_time="2013033123") for i in range(n_members)]
+    col = np.array([0, 0, 1, 1, 1, 0], dtype=np.int32)[:n_members]
+    m = BmiTopoflowGlacier()
+    m.initialize_ensemble(cfgs, forcing_index=col, n_forcing_cols=2)
+    return m, cfgs, col, z["forcing"]
+
+
+def test_bulk_bmi_path_with_forcing_map(cuda_device):
+    """update_steps / load_forcing + update_until on an ensemble built with forcing_index:
+    the block has one column per SERIES; equal to per-step update() bit for bit; held inputs work too; a block of
+    the wrong shape is rejected BEFORE the model advances; an exhausted queue raises instead of silently holding
+    the inputs constant."""
+    import torch
+
+    bulk, cfgs, col, forcing = _shared_ensemble()
+    step, _, _, _ = _shared_ensemble()
+    T = 30
+    f = np.ascontiguousarray(forcing[:T, :, :2])
+    f_dev = torch.as_tensor(f).cuda()
+    bulk.update_steps(10, f_dev[:10].contiguous())
+    bulk.load_forcing(f_dev[10:].contiguous())
+    bulk.update_until(25 * 3600.0)
+    names = ("atmosphere_water__liquid_equivalent_precipitation_rate", "land_surface_air__temperature",
+             "land_surface_air__pressure", "atmosphere_air_water~vapor__relative_saturation", "wind_speed_UV")
+    for t in range(25):
+        for j, name in enumerate(names):
+            step.set_value(name, f[t, j])
+        step.update()
+    a, b = np.zeros(6), np.zeros(6)
+    for name in bulk.get_output_var_names():
+        assert np.array_equal(bulk.get_value(name, a), step.get_value(name, b)), name
+    # the inputs reflect the last consumed step (one value per series)
+    assert np.array_equal(bulk.get_value("land_surface_air__temperature", np.zeros(2)), f[24, 1])
+    # held inputs over an interval == repeated update()
+    bulk._forcing_block = None
+    bulk.update_until(28 * 3600.0)
+    for _ in range(3):
+        step.update()
+    for name in bulk.get_output_var_names():
+        assert np.array_equal(bulk.get_value(name, a), step.get_value(name, b)), name
+    # wrong shape: rejected, model not advanced
+    now = bulk.get_current_time()
+    with pytest.raises(ValueError):
+        bulk.update_steps(2, torch.zeros(2, 5, 6, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        bulk.load_forcing(torch.zeros(2, 5, 6, dtype=torch.float64, device="cuda"))
+    assert bulk.get_current_time() == now
+    # exhausted queue: the remaining steps are consumed, then a loud error
+    bulk.load_forcing(f_dev[28:30].contiguous())
+    with pytest.raises(RuntimeError, match="held 2 more steps"):
+        bulk.update_until(now + 5 * 3600.0)
+    assert bulk.get_current_time() == now + 2 * 3600.0
+    bulk.finalize(), step.finalize()
+
+
+def test_back_to_back_set_update_without_reads(cuda_device):
+    """A driver that never reads outputs between steps (set_value x5, update, repeat): the pinned staging block is
+    re-written while the previous upload may still be in flight (bmi.py:157).  Large N (initialize_cells)
+    so that copies and kernels take long enough to run behind the host loop; compared with the fused run."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier import BmiTopoflowGlacier
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    N, T = 400_000, 40
+    statics, forcing = bench.synthetic_host_sample(N, T, seed=21)
+    m = BmiTopoflowGlacier()
+    m.initialize_cells(dict(SAMPLE_CONFIG, start_time="2013040100", utc_offset_hours=-8.0, precision="f64_fast"), statics)
+    assert m.get_grid_size(0) == N and m.get_var_nbytes("snowpack__depth") == 8 * N
+    ref = MeltEngine(statics, default_constants(), "2013040100", zones=[-8.0], mode="f64_fast", horizon_steps=T + 2)
+    ref.run(torch.as_tensor(forcing).cuda())
+    for t in range(T):
+        for j, name in enumerate(SET_ORDER):
+            m.set_value(name, forcing[t, j])
+        m.update()
+    got = {name: m.get_value(name, np.zeros(N)).copy() for name in m.get_output_var_names()}
+    # update() re-sums the snowfall window exactly every step, the fused run incrementally: decisions are identical
+    for name, k in (("snowpack__liquid-equivalent_depth", "h_swe"), ("glacier__liquid_equivalent_depth", "h_iwe"),
+                    ("land_surface_water__runoff_volume_flux", "M_total"), ("snowpack__depth", "h_snow"),
+                    ("atmosphere_bottom_air_water-vapor__relative_saturation", "RH")):
+        assert np.array_equal(got[name], ref.row(k).cpu().numpy()), name
+    m.finalize(), ref.close()
+
+
+def test_bmi_index_access_grid_and_time_queries(tmp_path, cuda_device):
+    """get/set_value_at_indices, get_grid_shape, get_end_time, get_var_location, get_var_grid (VERDICT r1 weak #10;
+    reference bmi_topoflow_glacier.py:1804-1808, context.py:47-59; they raise in the reference's base class)."""
+    m, cfgs, col, forcing = _shared_ensemble()
+    n = len(cfgs)
+    assert m.get_end_time() == (11 * 24 + 23) * 3600.0 and m.get_start_time() == 0
+    assert m.get_grid_rank(0) == 1 and m.get_grid_size(0) == n and m.get_grid_node_count(0) == n
+    assert m.get_grid_type(0) == "points"
+    shape = np.zeros(1, dtype=np.int64)
+    assert m.get_grid_shape(0, shape) is shape and shape[0] == n
+    assert m.get_var_location("snowpack__depth") == "node" and m.get_var_grid("wind_speed_UV") == 0
+    with pytest.raises(KeyError):
+        m.get_var_location("nope")
+    # outputs: set single members, read them back through both accessors
+    name = "snowpack__liquid-equivalent_depth"
+    before = m.get_value(name, np.zeros(n)).copy()
+    m.set_value_at_indices(name, np.array([1, 4]), np.array([0.125, 0.5]))
+    after = m.get_value(name, np.zeros(n))
+    want = before.copy()
+    want[[1, 4]] = (0.125, 0.5)
+    assert np.array_equal(after, want)
+    got = m.get_value_at_indices(name, np.zeros(3), np.array([4, 0, 1]))
+    assert np.array_equal(got, want[[4, 0, 1]])
+    assert np.array_equal(m.get_value_ptr(name).cpu().numpy(), want)      # the live device tensor saw the write
+    # inputs hold one value per forcing series (2)
+    t_name = "land_surface_air__temperature"
+    m.set_value(t_name, np.array([1.5, -3.0]))
+    m.set_value_at_indices(t_name, np.array([1]), np.array([-7.25]))
+    assert np.array_equal(m.get_value(t_name, np.zeros(2)), [1.5, -7.25])
+    assert np.array_equal(m.get_value_at_indices(t_name, np.zeros(1), np.array([1])), [-7.25])
+    m.update()                                                             # and the kernel consumed it
+    assert m.get_current_time() == 3600.0
+    single = _model(tmp_path, SAMPLE_CONFIG)
+    assert single.get_grid_type(0) == "scalar" and single.get_end_time() == 11 * 24 * 3600.0
+    single.finalize(), m.finalize()
+
+
+def test_sharded_engine_single_rank_equals_plain_engine(cuda_device):
+    """ShardedMeltEngine without a process group == MeltEngine + BasinAggregates; cells from a factory too."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.sharding import BasinAggregates, ShardedMeltEngine
+
+    N, T, NB = 3000, 9, 11
+    statics, forcing = bench.synthetic_host_sample(N, T, seed=8)
+    basin = (np.arange(N) * NB // N).astype(np.int32)
+    f = torch.as_tensor(forcing).cuda()
+    kw = dict(zones=[-8.0], mode="f64_fast", horizon_steps=T + 1)
+    plain = MeltEngine(statics, default_constants(), "2013040100", basin_id=basin, n_basin=NB, **kw)
+    agg = BasinAggregates(T, NB, device=cuda_device, exponents=plain.agg_exponents())
+    plain.run(f, basin_agg=agg.zero())
+    agg.reduce()
+    sh = ShardedMeltEngine(statics, default_constants(), "2013040100", basin_id=basin, n_basin=NB, **kw)
+    assert sh.bounds == (0, N) and sh.world == 1
+    _, got = sh.run(sh.local(f).contiguous())
+    fac = ShardedMeltEngine(lambda lo, hi: {k: v[lo:hi] for k, v in statics.items()}, default_constants(), "2013040100",
+                            n_total=N, basin_id=lambda lo, hi: basin[lo:hi], n_basin=NB, **kw)
+    _, got2 = fac.run(f)
+    torch.cuda.synchronize()
+    assert torch.equal(got, agg.buffer) and torch.equal(got2, agg.buffer)
+    assert torch.equal(sh.state, plain.state)
+    np.testing.assert_allclose(sh.basin_area().cpu().numpy(), np.bincount(basin, weights=statics["da"] * 1e6), rtol=1e-14)
+    for e in (plain, sh, fac):
+        e.close()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_engine_two_ranks_equal_one(tmp_path, cuda_device):
+    """Two ranks (one process each; gloo carries the collectives so that both may share the one GPU of the test box)
+    driving ShardedMeltEngine / BmiTopoflowGlacier.initialize_cells(shard=True): the global exact aggregates are
+    bit-identical to a single engine over all cells, and the shards' states are the single engine's rows."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.sharding import BasinAggregates
+
+    N, T, NB = 5000, 14, 13
+    statics, forcing = bench.synthetic_host_sample(N, T, seed=12)
+    rng = np.random.default_rng(4)
+    basin = rng.integers(0, NB, N).astype(np.int32)
+    basin[500:3000] = np.sort(basin[500:3000])
+    np.savez(tmp_path / "in.npz", forcing=forcing, basin=basin, **{f"s_{k}": v for k, v in statics.items()})
+    one = MeltEngine(statics, default_constants(), "2013040100", zones=[-8.0], mode="f64_fast", basin_id=basin,
+                     n_basin=NB, horizon_steps=T + 1)
+    agg = BasinAggregates(T, NB, device=cuda_device, exponents=one.agg_exponents())
+    one.run(torch.as_tensor(forcing).cuda(), basin_agg=agg.zero())
+    agg.reduce()
+    torch.cuda.synchronize()
+    root = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    script = tmp_path / "w.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+os.environ["NGEN_EWTS_LOGGING"] = "DISABLED"
+import numpy as np, torch, torch.distributed as dist
+from topoflow_glacier_b200.config import default_constants
+from topoflow_glacier_b200.sharding import ShardedMeltEngine
+from topoflow_glacier import BmiTopoflowGlacier
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+z = np.load({str(tmp_path / "in.npz")!r})
+statics = {{k[2:]: z[k] for k in z.files if k.startswith("s_")}}
+f = torch.as_tensor(z["forcing"]).cuda()
+T = f.shape[0]
+sh = ShardedMeltEngine(statics, default_constants(), "2013040100", zones=[-8.0], mode="f64_fast", basin_id=z["basin"],
+                       n_basin={NB}, horizon_steps=T + 1, device=0)
+done, parts = 0, []
+for k in (5, T - 5):            # two launches: the aggregate buffers are per launch length
+    _, g = sh.run(sh.local(f[done:done + k]).contiguous())
+    parts.append(g.clone()); done += k
+# the same through the BMI surface
+cfg = dict(site_prefix="x", forcing_file="-", dt=1, start_time="2013040100", end_time="2013041000", da=1.0, slope=1.0,
+           lat=46.0, lon=-121.0, h0_snow=0.0, h0_ice=0.0, h0_swe=0.0, h0_iwe=0.0, elev=1.0, utc_offset_hours=-8.0,
+           precision="f64_fast")
+m = BmiTopoflowGlacier()
+m.initialize_cells(cfg, statics, shard=True, basin_id=z["basin"], n_basin={NB}, device=0)
+lo, hi = m.sharded.bounds
+assert m.get_grid_size(0) == hi - lo and len(m.da_m2) == hi - lo
+m.update_steps(T, m.sharded.local(f).contiguous())
+torch.cuda.synchronize()
+assert torch.equal(m._engine.state, sh.state)
+np.savez({str(tmp_path)!r} + f"/out{{rank}}.npz", agg=torch.cat(parts).cpu().numpy(), state=sh.state.cpu().numpy(),
+         lo=lo, hi=hi)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, env=env, timeout=560)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    outs = [np.load(tmp_path / f"out{k}.npz") for k in range(2)]
+    want = agg.buffer.cpu().numpy()
+    for o in outs:
+        assert np.array_equal(o["agg"], want)                      # global sums on every rank, bit for bit
+        assert np.array_equal(o["state"], one.state[:, int(o["lo"]):int(o["hi"])].cpu().numpy())
+    assert int(outs[0]["hi"]) == int(outs[1]["lo"]) and int(outs[1]["hi"]) == N
+    one.close()

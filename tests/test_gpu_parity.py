@@ -391,3 +391,41 @@ def test_engine_argument_errors(cuda_device):
     eng.run(good)
     assert eng.step_index == 4
     eng.close()
+
+
+@pytest.mark.parametrize("chunk", [0, 16])
+@pytest.mark.parametrize("mode", ["f64", "f64_fast"])
+def test_window_sum_recovers_from_missing_precipitation(mode, chunk, cuda_device):
+    """A missing (NaN) or absurd (inf) precipitation value poisons the 3-day snowfall total only while it is inside the
+    72-slot window -- the reference re-sums the window every step (:1035-1037), so `n` resumes counting 72 steps
+    later.  The fused kernel keeps a running sum: it must fall back to the exact re-sum while the sum is not finite
+    (tfg_run.cuh:334), for one launch and for launches that carry the running sum between them."""
+    import torch
+
+    case = load_case("cats288")
+    T = 120
+    f = case["forcing"][:T].copy()
+    f[:, 1] = -4.0                       # snowfall
+    f[:, 0] = 2e-5
+    f[7, 0, 0] = np.nan                  # cell 0: one missing value
+    f[9, 0, 1] = np.inf                  # cell 1: +inf enters, inf - inf = NaN when it leaves the window
+    c2 = dict(case, forcing=f)
+    want = make_oracle(c2, strict_pow=True).run(f, record=("n", "snow3day"))
+    eng = make_engine(c2, mode=mode)
+    f_dev = torch.as_tensor(f).cuda()
+    if chunk:
+        parts = [eng.run(f_dev[t0:t0 + chunk].contiguous(), record=("n", "snow3day")) for t0 in range(0, T, chunk)]
+        got = {k: torch.cat([p[k] for p in parts]).cpu().numpy() for k in parts[0]}
+    else:
+        got = {k: v.cpu().numpy() for k, v in eng.run(f_dev, record=("n", "snow3day")).items()}
+    eng.close()
+    assert np.isnan(want["snow3day"][7:79, 0]).all() and np.isfinite(want["snow3day"][79:, 0]).all()
+    assert np.isfinite(want["snow3day"][81:, 1]).all()
+    for k in ("n", "snow3day"):
+        assert np.array_equal(np.isnan(got[k]), np.isnan(want[k])), k
+        assert np.array_equal(np.isinf(got[k]), np.isinf(want[k])), k
+    ok = np.isfinite(want["snow3day"])
+    np.testing.assert_allclose(got["snow3day"][ok], want["snow3day"][ok], rtol=1e-12, atol=1e-13)
+    assert np.array_equal(got["n"][:, 2:], want["n"][:, 2:])                      # untouched cells: exact
+    np.testing.assert_array_equal(got["n"][ok[:, 0], 0], want["n"][ok[:, 0], 0])  # poisoned cells: exact once clean
+    np.testing.assert_array_equal(got["n"][ok[:, 1], 1], want["n"][ok[:, 1], 1])

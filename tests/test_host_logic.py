@@ -120,9 +120,14 @@ def test_shard_bounds_cover_all_cells():
 
     for n in (1, 4, 127, 128, 100_000_000, 16_777_216, 12345):
         for world in (1, 2, 3, 4, 8):
+            if -(-n // 128) < world:  # fewer 128-cell groups than ranks: a rank without cells would hang the
+                with pytest.raises(ValueError):  # collectives of the others -> loud error instead
+                    shard_sizes(n, world)
+                continue
             sizes = shard_sizes(n, world)
-            assert sum(sizes) == n and all(s >= 0 for s in sizes)
-            assert all(s % 128 == 0 for s in sizes[:-1] if s and sizes[-1])
+            assert sum(sizes) == n and all(s > 0 for s in sizes)
+            assert all(s % 128 == 0 for s in sizes[:-1])
+            assert max(sizes) - min(sizes) <= 128 + 127   # dealt out evenly: at most one group (+ the partial one) apart
             hi_prev = 0
             for r in range(world):
                 lo, hi = shard_bounds(n, world, r)

@@ -103,6 +103,27 @@ class BmiTopoflowGlacier(_BmiBase):
         self.cfg = cfgs[0]
         self._build(cfgs, **engine_kw)
 
+    def initialize_cells(self, base_config, cells, zones=None, tz_idx=None, **engine_kw) -> None:
+        """Extension: N cells given as arrays (a raster, elevation bands ...) instead of N yaml files.
+
+        ``base_config`` (path, dict or validated object) supplies ``dt``, the time window and the physical constants;
+        ``cells`` maps the per-catchment yaml keys (``statics.CELL_KEYS``: ``da, slope, aspect, lon, lat, elev,
+        h0_snow, h0_ice, h0_swe, h0_iwe, T_rain_snow``) to float64 ``[N]`` arrays.  ``zones`` / ``tz_idx`` as for
+        ``MeltEngine``; ``engine_kw`` reaches it too (``mode``, ``basin_id``, ``n_basin``, ``forcing_index`` ...).
+        With ``shard=True`` under an initialised ``torch.distributed`` group every rank keeps only its own
+        128-aligned block of the cells (``sharding.shard_bounds``) -- see ``ShardedMeltEngine``."""
+        c = base_config
+        if isinstance(c, (str, Path)):
+            with open(c) as f:
+                c = yaml.safe_load(f)
+        self.cfg = c if isinstance(c, TopoflowGlacierConfig) else TopoflowGlacierConfig.model_validate(c)
+        cells = {k: np.atleast_1d(np.asarray(cells[k], dtype=np.float64)) for k in CELL_KEYS}
+        if zones is None:
+            h = self.cfg
+            zones = [h.utc_offset_hours if h.utc_offset_hours is not None else
+                     (h.tz_name or default_timezone(float(cells["lat"].mean()), float(cells["lon"].mean())))]
+        self._build_from_cells(self.cfg, cells, list(zones), tz_idx, **engine_kw)
+
     def _build(self, cfgs, **engine_kw) -> None:
         head = cfgs[0]
         for c in cfgs[1:]:
@@ -115,11 +136,17 @@ class BmiTopoflowGlacier(_BmiBase):
             if z not in zones:
                 zones.append(z)
             tz_idx[i] = zones.index(z)
+        for z in zones:  # the zone is data here (the reference looks it up): say which one was taken
+            logger.info(f"time zone / UTC offset in use: {z}")
+        self._build_from_cells(head, cells, zones, tz_idx if len(zones) > 1 else None, **engine_kw)
+
+    def _build_from_cells(self, head, cells, zones, tz_idx, shard: bool = False, **engine_kw) -> None:
+        n_total = int(cells["lat"].size)
         # reference scalars drivers rely on (:286-294)
         self.dt = head.dt
         self.C_to_K = 273.15
         self.K_to_C = -273.15
-        self.da_km2 = head.da if len(cfgs) == 1 else cells["da"]
+        self.da_km2 = head.da if n_total == 1 else cells["da"]
         self.da_m2 = self.da_km2 * 1e6
         self._start = parse_start(head.start_time)
         try:
@@ -130,14 +157,27 @@ class BmiTopoflowGlacier(_BmiBase):
         engine_kw.setdefault("mode", head.precision)
         engine_kw.setdefault("device", head.device)
         engine_kw.setdefault("horizon_steps", horizon)
-        self._engine = MeltEngine(cells, head.model_dump(), head.start_time, dt_hours=head.dt, zones=zones,
-                                  tz_idx=tz_idx if len(zones) > 1 else None, **engine_kw)
+        if shard:
+            from .sharding import ShardedMeltEngine
+
+            # every rank keeps its block of the cells; BMI variables then hold this rank's cells only, and
+            # `model.sharded.run(...)` returns the global basin aggregates (sharding.ShardedMeltEngine)
+            self.sharded = ShardedMeltEngine(cells, head.model_dump(), head.start_time, dt_hours=head.dt, zones=zones,
+                                             tz_idx=tz_idx, **engine_kw)
+            self._engine = self.sharded.engine
+            lo, hi = self.sharded.bounds
+            self.da_km2 = cells["da"][lo:hi]
+            self.da_m2 = self.da_km2 * 1e6
+        else:
+            self._engine = MeltEngine(cells, head.model_dump(), head.start_time, dt_hours=head.dt, zones=zones,
+                                      tz_idx=tz_idx, **engine_kw)
         e = self._engine
         self._n = e.N
         # pinned staging: inputs (upload at update) and outputs (download at first get after update)
         # (one column per cell, or per forcing column when the ensemble was built with forcing_index=...)
         self._in_host = torch.zeros(len(INPUT_ROWS), e.n_cols, dtype=e.dtype).pin_memory()
         self._in_dirty = np.zeros(len(INPUT_ROWS), dtype=bool)
+        self._in_uploaded = None  # CUDA event: the last asynchronous upload has finished reading _in_host
         self._out_host = torch.zeros(len(_OUT_INTERNAL), e.N, dtype=e.dtype).pin_memory()
         self._out_rows = torch.tensor([self._state_row(k) for k in _OUT_INTERNAL], device=e.device)
         self._out_valid = False
@@ -159,6 +199,16 @@ class BmiTopoflowGlacier(_BmiBase):
                 for r in np.flatnonzero(self._in_dirty):
                     e.inputs[r].copy_(self._in_host[r], non_blocking=True)
             self._in_dirty[:] = False
+            # the DMA reads the pinned block asynchronously: the next host write into it must wait for this event
+            self._in_uploaded = torch.cuda.Event()
+            self._in_uploaded.record(torch.cuda.current_stream(e.device))
+
+    def _wait_upload(self) -> None:
+        """Block until the pinned input block may be overwritten (a driver that calls set_value / update in a loop
+        without reading outputs would otherwise overwrite values an upload in flight has not read yet)."""
+        if self._in_uploaded is not None:
+            self._in_uploaded.synchronize()
+            self._in_uploaded = None
 
     def update(self) -> None:
         """Advance one timestep from the current inputs (reference ``update()``, ``:413-465``)."""
@@ -174,15 +224,23 @@ class BmiTopoflowGlacier(_BmiBase):
         ``update_until`` loop does (``:489-490``).
         """
         e = self._engine
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            raise ValueError("n_steps must be positive")
+        if forcing is not None and (forcing.dim() != 3 or forcing.shape[0] < n_steps or
+                                    tuple(forcing.shape[1:]) != (5, e.n_cols)):
+            # checked BEFORE the launch: a bad block must not leave the model advanced
+            raise ValueError(f"forcing must be [>= {n_steps}, 5, {e.n_cols}] (one column per "
+                             f"{'forcing series' if e.forcing_index is not None else 'cell'}), got {tuple(forcing.shape)}")
         self._flush_inputs()
         self._out_valid = False
         if forcing is not None:
             out = e.run(forcing, n_steps, **run_kw)
-            e.inputs[:5].copy_(forcing[n_steps - 1].reshape(5, e.N))  # inputs reflect the last step
+            e.inputs[:5].copy_(forcing[n_steps - 1])  # inputs reflect the last step
             return out
         out, done = {}, 0
-        chunk = max(1, min(n_steps, (64 << 20) // max(1, 5 * e.N * e.inputs.element_size())))
-        block = e.inputs[:5].unsqueeze(0).expand(chunk, 5, e.N).contiguous()
+        chunk = max(1, min(n_steps, (64 << 20) // max(1, 5 * e.n_cols * e.inputs.element_size())))
+        block = e.inputs[:5].unsqueeze(0).expand(chunk, 5, e.n_cols).contiguous()
         while done < n_steps:
             k = min(chunk, n_steps - done)
             part = e.run(block, k, **run_kw)
@@ -192,7 +250,11 @@ class BmiTopoflowGlacier(_BmiBase):
         return {k: torch.cat(v) for k, v in out.items()}
 
     def load_forcing(self, forcing: torch.Tensor) -> None:
-        """Extension: queue a device-resident ``[T, 5, N]`` block that ``update_until`` consumes step by step."""
+        """Extension: queue a device-resident ``[T, 5, N]`` block (``[T, 5, n_series]`` for an ensemble built with
+        ``forcing_index``) that ``update_until`` consumes step by step."""
+        e = self._engine
+        if forcing.dim() != 3 or tuple(forcing.shape[1:]) != (5, e.n_cols):
+            raise ValueError(f"forcing must be [T, 5, {e.n_cols}], got {tuple(forcing.shape)}")
         self._forcing_block, self._forcing_pos = forcing, 0
 
     def update_until(self, time: float) -> None:
@@ -208,11 +270,17 @@ class BmiTopoflowGlacier(_BmiBase):
         if n_steps <= 0:
             return None
         fb = self._forcing_block
-        if fb is not None and fb.shape[0] - self._forcing_pos >= n_steps:
-            self.update_steps(n_steps, fb[self._forcing_pos:self._forcing_pos + n_steps])
-            self._forcing_pos += n_steps
-        else:
-            self.update_steps(n_steps)
+        if fb is None:
+            self.update_steps(n_steps)   # inputs held constant, as the reference's loop of update() calls (:489-490)
+            return None
+        left = fb.shape[0] - self._forcing_pos
+        k = min(left, n_steps)
+        if k > 0:
+            self.update_steps(k, fb[self._forcing_pos:self._forcing_pos + k])
+            self._forcing_pos += k
+        if k < n_steps:  # never fall back silently to constant inputs in the middle of a queued series
+            raise RuntimeError(f"update_until({time}): the block queued by load_forcing held {left} more steps, "
+                               f"{n_steps} were requested; the model stopped at t = {self.get_current_time()} s")
 
     # ------------------------------------------------------------------ checkpoint / resume (extension)
     def save_state(self, path) -> None:
@@ -221,6 +289,7 @@ class BmiTopoflowGlacier(_BmiBase):
 
     def load_state(self, path) -> None:
         self._engine.load_state_dict(torch.load(path, weights_only=False))
+        self._wait_upload()
         self._in_host.copy_(self._engine.inputs)
         self._in_dirty[:] = False
         self._out_valid = False
@@ -319,6 +388,7 @@ class BmiTopoflowGlacier(_BmiBase):
         if internal in INPUT_ROWS:
             r = INPUT_ROWS.index(internal)
             if not self._in_dirty[r]:
+                self._wait_upload()
                 self._in_host[r].copy_(self._engine.inputs[r])
             return self._in_host[r].numpy()
         if not self._out_valid:
@@ -346,6 +416,7 @@ class BmiTopoflowGlacier(_BmiBase):
         internal = self._internal(name)
         if internal in INPUT_ROWS:
             r = INPUT_ROWS.index(internal)
+            self._wait_upload()
             self._in_host[r].numpy()[:] = src
             self._in_dirty[r] = True
         else:

@@ -331,12 +331,17 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
           // the incremental sum drifts by < 330 roundings of the largest sum seen during a launch (72 seed
           // additions + 2 per step, <= 128 steps): below 1e4 m that is < 4e-10 m, so a fixed band around the
           // threshold suffices; larger sums (absurd forcing) take the exact path every step
-          near_threshold = (nabs(tot - LIT(snow_thr, 0.03)) <= 1e-9) || (__double2hiint(tot.v) >= 0x40c38800);
+          // (the magnitude test on the high word also catches NaN / inf of either sign: a non-finite entry must
+          // poison the sum only while it is inside the window, as in the reference's re-summation every step)
+          near_threshold = (nabs(tot - LIT(snow_thr, 0.03)) <= 1e-9) ||
+                           (((unsigned)__double2hiint(tot.v) & 0x7fffffffu) >= 0x40c38800u);
         } else {
           // drift bound: (seed additions + 2 per step) roundings of the largest sum seen since the last exact sum
           tot_hi = nmax(tot_hi, nabs(tot));
           n_round = n_round + R(2.0);
-          near_threshold = nabs(tot - 0.03) <= (guard * n_round) * tot_hi;
+          // !(x <= y) instead of x > y: a non-finite running sum (NaN compares false) takes the exact path too, so
+          // that it recovers as soon as the bad entry has left the window (as the reference's per-step re-sum does)
+          near_threshold = !(nabs(tot - 0.03) > (guard * n_round) * tot_hi) || !(nabs(tot) < R(1e30));
         }
         if (near_threshold) {
           tot = window_sum_exact<P>(ring, N, slots, slot);

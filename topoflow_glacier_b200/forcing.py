@@ -75,6 +75,8 @@ class ForcingStreamer:
         self.e = engine
         self.Tc = int(chunk_steps)
         self.nb = int(n_buffers)
+        if self.nb < 2:  # piece k+1 is uploaded while piece k is being consumed: one buffer would be overwritten
+            raise ValueError("ForcingStreamer needs n_buffers >= 2")
         N, dev = engine.n_cols, engine.device   # forcing columns (= cells unless the engine has a forcing map)
         self.N = N
         self.side = torch.cuda.Stream(device=dev)

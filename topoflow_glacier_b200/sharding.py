@@ -14,22 +14,33 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_sizes", "BasinAggregates", "basin_sums_host", "dist_info"]
+__all__ = ["shard_bounds", "shard_sizes", "BasinAggregates", "basin_sums_host", "dist_info", "ShardedMeltEngine"]
 
 AGG_NAMES = ("runoff_m3s", "swe_m3", "iwe_m3")  # sum(M_total*da_m2), sum(h_swe*da_m2), sum(h_iwe*da_m2)
 
 
 def shard_sizes(n_cells: int, world: int, align: int = 128) -> list[int]:
-    """Cells per rank: contiguous blocks, every block but the last a multiple of ``align`` cells."""
-    if world < 1 or n_cells < 0:
-        raise ValueError("bad world size / cell count")
-    per = -(-n_cells // world)
-    per = -(-per // align) * align
-    sizes, left = [], n_cells
-    for _ in range(world):
-        k = min(per, left)
-        sizes.append(k)
-        left -= k
+    """Cells per rank: contiguous blocks, every block but the last a multiple of ``align`` cells.
+
+    The ``align``-cell groups are dealt out as evenly as possible (sizes differ by at most one group), so no rank is
+    left without cells while another holds several groups; fewer groups than ranks is an error -- a rank with zero
+    cells would sit out the collectives of the others."""
+    if world < 1 or n_cells < 0 or align < 1:
+        raise ValueError("bad world size / cell count / alignment")
+    groups = -(-n_cells // align)
+    if n_cells > 0 and groups < world:
+        raise ValueError(f"{n_cells} cells are {groups} groups of {align}: too few to give each of {world} ranks a share")
+    base, extra = divmod(groups, world)
+    sizes = [(base + (1 if r < extra else 0)) * align for r in range(world)]
+    over = sum(sizes) - n_cells          # the last group may be partial; with extra < world it may sit mid-list
+    for r in range(world - 1, -1, -1):
+        if over <= 0:
+            break
+        cut = min(over, sizes[r])
+        sizes[r] -= cut
+        over -= cut
+    if n_cells > 0 and min(sizes) <= 0:
+        raise ValueError(f"sharding {n_cells} cells over {world} ranks leaves a rank without cells")
     return sizes
 
 
@@ -134,3 +145,96 @@ class BasinAggregates:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(area, op=dist.ReduceOp.SUM, group=self.group)
         return area
+
+
+class ShardedMeltEngine:
+    """The ensemble of ALL cells advanced by all ranks of a ``torch.distributed`` group, one shard per GPU.
+
+    The multi-GPU counterpart of ``MeltEngine`` for users of the product API (``bench.py`` uses it too): every rank
+    constructs it with the same arguments, keeps the 128-aligned contiguous block ``bounds = shard_bounds(n_total,
+    world, rank)`` of the cells on its own GPU, and ``run`` returns the GLOBAL per-basin aggregates -- the only
+    quantity that crosses GPUs on this path (reference ``np.sum`` sites ``bmi_topoflow_glacier.py:567-568,
+    :1486-1494`` and the driver's ``* da_m2``, ``examples/run_topoflow_glacier.py:115``).  With ``exact=True``
+    (default) the sums are order-independent fixed-point accumulators: 1, 2, 4 or 8 GPUs return the same bits.
+
+    ``cells`` is either the mapping of GLOBAL float64 ``[n_total]`` arrays ``MeltEngine`` takes (sliced here), or a
+    callable ``(lo, hi) -> mapping`` that produces the shard's arrays (host arrays keyed like ``cells``, or device
+    tables keyed like ``tfg_statics`` + ``h0_*``) for grids too large to materialise on every rank; then pass
+    ``n_total``.  ``basin_id`` / ``tz_idx`` / ``forcing_index`` are global arrays (or callables ``(lo, hi)``).
+    Attribute access falls through to the local ``MeltEngine`` (``state``, ``row``, ``step_index`` ...).
+    """
+
+    def __init__(self, cells, consts, start_time, *, n_total: Optional[int] = None, basin_id=None, n_basin: int = 0,
+                 tz_idx=None, forcing_index=None, group=None, exact: bool = True, device: Optional[int] = None, **kw):
+        import os
+
+        import torch
+
+        from .engine import MeltEngine
+
+        self.group = group
+        try:
+            import torch.distributed as dist
+
+            on = dist.is_available() and dist.is_initialized()
+            self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+        except ImportError:
+            self.rank, self.world = 0, 1
+        if callable(cells):
+            if n_total is None:
+                raise ValueError("n_total is required when cells is a factory")
+        else:
+            n_total = int(np.size(cells["lat"]))
+        self.n_total = int(n_total)
+        lo, hi = shard_bounds(self.n_total, self.world, self.rank)
+        self.bounds = (lo, hi)
+        part = (lambda a: None if a is None else (a(lo, hi) if callable(a) else a[lo:hi]))
+        local = cells(lo, hi) if callable(cells) else {k: np.asarray(v)[lo:hi] for k, v in cells.items()}
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", self.rank)) % max(torch.cuda.device_count(), 1)
+        dev_tables = "a_elev" in local
+        self.exact = bool(exact)
+        self.engine = MeltEngine(None if dev_tables else local, consts, start_time, basin_id=part(basin_id),
+                                 n_basin=n_basin, tz_idx=part(tz_idx), forcing_index=part(forcing_index), device=device,
+                                 device_statics=local if dev_tables else None, **kw)
+        self._aggs: dict = {}
+
+    def __getattr__(self, name):
+        if name == "engine":
+            raise AttributeError(name)
+        return getattr(self.engine, name)
+
+    def local(self, global_block):
+        """This rank's columns ``[..., lo:hi]`` of a per-cell array or forcing block laid out over ALL cells."""
+        lo, hi = self.bounds
+        return global_block[..., lo:hi]
+
+    def aggregates(self, n_steps: int) -> BasinAggregates:
+        """The (cached) aggregate buffers for launches of ``n_steps`` timesteps."""
+        a = self._aggs.get(n_steps)
+        if a is None:
+            exps = self.engine.agg_exponents() if self.exact else None   # collective: all ranks get here together
+            a = self._aggs[n_steps] = BasinAggregates(n_steps, self.engine.n_basin, device=self.engine.device,
+                                                      group=self.group, exponents=exps)
+        return a
+
+    def run(self, forcing, n_steps: Optional[int] = None, record=None, aggregate: bool = True):
+        """Advance the local shard and combine the basin aggregates over all ranks.
+
+        ``forcing`` is this rank's block ``[T, 5, n_local]`` (``[T, 5, n_forcing_cols]`` with a forcing map).
+        Returns ``(records, agg)``: the local recorded series and the GLOBAL ``[T, n_basin, 3]`` float64 sums
+        (``None`` when the engine has no basins or ``aggregate=False``); the buffer is reused by the next call."""
+        T = int(n_steps if n_steps is not None else forcing.shape[0])
+        if not aggregate or self.engine.n_basin <= 0 or self.engine.basin_id is None:
+            return self.engine.run(forcing, T, record=record), None
+        agg = self.aggregates(T)
+        rec = self.engine.run(forcing, T, record=record, basin_agg=agg.zero())
+        agg.reduce()
+        return rec, agg.buffer
+
+    def basin_area(self):
+        """Global per-basin area ``sum(da_m2)`` (all ranks)."""
+        return self.aggregates(1).basin_area(self.engine.static["da_m2"], self.engine.basin_id)
+
+    def close(self):
+        self.engine.close()
