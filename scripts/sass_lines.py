@@ -37,6 +37,7 @@ def main() -> None:
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--via", help="only instructions inlined through a tfg_run.cuh line containing this text")
     ap.add_argument("--ops", action="store_true", help="also print the opcode histogram of the selected instructions")
+    ap.add_argument("--by-samples", action="store_true", help="rank source lines by warp-stall samples (time) instead of FP64 count")
     a = ap.parse_args()
 
     text = disasm(a.obj)
@@ -79,20 +80,25 @@ def main() -> None:
                 book = chain[-1] if chain else ("?", 0)
             insts.append((int(m.group(1), 16), m.group(2), book))
 
-    dyn = None
+    dyn = smp = None
     if a.ncu_csv:
         rows = list(csv.reader(open(a.ncu_csv)))
         hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
         col = rows[hdr].index("Instructions Executed")
         base = int(rows[hdr + 1][0], 16)
         dyn = {int(r[0], 16) - base: int(r[col]) for r in rows[hdr + 1:] if r and r[0].startswith("0x")}
+        scol = rows[hdr].index("# Samples")
+        smp = {int(r[0], 16) - base: int(r[scol]) for r in rows[hdr + 1:] if r and r[0].startswith("0x")}
 
     tot = collections.Counter()
+    stall = collections.Counter()
     fp = collections.Counter()
     ops = collections.Counter()
     for off, op, book in insts:
         w = dyn.get(off, 0) if dyn is not None else 1
         tot[book] += w
+        if smp is not None:
+            stall[book] += smp.get(off, 0)
         ops[op.split(".")[0]] += w
         if op.startswith(FP64):
             fp[book] += w
@@ -102,11 +108,15 @@ def main() -> None:
         src[f] = (ROOT / "topoflow_glacier_b200" / "csrc" / f).read_text().splitlines()
     print(f"kernel {a.kernel}: {len(insts)} SASS instructions; {'dynamic' if dyn else 'static'} totals: all={all_t} fp64={all_f}")
     ranked = fp if all_f > 0.05 * all_t else tot  # float32 kernels have (almost) no FP64 instructions: rank by all
+    if a.by_samples and smp is not None:
+        ranked = stall
+    all_s = max(sum(stall.values()), 1)
     for book, _ in sorted(ranked.items(), key=lambda kv: -kv[1])[: a.top]:
         n = fp[book]
         f, l = book
         s = src.get(f, [""] * (l + 1))[l - 1].strip()[:90] if f in src else ""
-        print(f"{100 * n / max(all_f, 1):5.1f}% fp64 {n:>12} | all {tot[book]:>12} | {f}:{l}  {s}")
+        extra = f" | {100 * stall[book] / all_s:5.1f}% of warp-stall samples" if smp is not None else ""
+        print(f"{100 * n / max(all_f, 1):5.1f}% fp64 {n:>12} | all {tot[book]:>12} ({100 * tot[book] / max(all_t, 1):4.1f}%){extra} | {f}:{l}  {s}")
     if a.ops:
         print("opcodes:", ", ".join(f"{k} {v}" for k, v in ops.most_common(25)))
 

@@ -22,6 +22,8 @@ ARRAY_FN(mc_atan_core, atan_core(a))
 ARRAY_FN(mc_stull, stull_wet_bulb(a, b))
 ARRAY_FN(mc_atan_diff, atan_diff(a, b))
 ARRAY_FN(mc_root7, root7(a, (float)b))
+ARRAY_FN(mc_stull_tab, stull_wet_bulb_tab(a, b))
+ARRAY_FN(mc_inv_air_mass, inv_air_mass(a))
 // the N-at-once variants must return exactly what the scalar routines return
 extern "C" void mc_exp_tab_2(const double* x, const double* y, double* out, long n) {
   for (long i = 0; i + 1 < n; i += 2) { const double a[2] = {x[i], x[i + 1]}; double r[2]; exp_tab_n<2>(a, r); out[i] = r[0]; out[i + 1] = r[1]; }

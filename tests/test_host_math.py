@@ -104,6 +104,32 @@ def test_arctangents_and_wet_bulb(lib):
     assert np.max(np.abs(call(lib, "mc_stull", T, RH).astype(L) - want)) < 5e-14   # |T| * 1 ulp of the arctangent
 
 
+def test_table_driven_wet_bulb_and_air_mass(lib):
+    """Round 2: piecewise-polynomial tables (scripts/gen_math_coeffs.py) for the Stull wet bulb and the Kasten-Young
+    air mass against the closed forms in 80-bit arithmetic."""
+    rng = np.random.default_rng(7)
+    T = np.concatenate([rng.uniform(-95, 95, 400_000), rng.uniform(-3, 3, 200_000)])
+    RH = np.concatenate([rng.uniform(3 / 64, 2, 500_000), rng.uniform(0.2, 1.1, 100_000)])
+    RH[:66] = np.concatenate([np.arange(1, 33) / 16.0, (np.arange(1, 33) + 0.5) / 16.0, [3 / 64, 2.0]])  # bin centres / edges
+    Tl, Rl = T.astype(L), RH.astype(L)
+    want = (Tl * np.arctan(L(0.151977) * np.sqrt(Rl + L(8.313659))) + np.arctan(Tl + Rl) - np.arctan(Rl - L(1.676331))
+            + L(0.00391838) * Rl ** L(1.5) * np.arctan(L(0.023101) * Rl) - L(4.86035))
+    got = call(lib, "mc_stull_tab", T, RH)
+    assert np.max(np.abs(got.astype(L) - want)) < 3e-14
+    # ... and it agrees with the closed-form fast routine it replaces to the same level
+    assert np.max(np.abs(got - call(lib, "mc_stull", T, RH))) < 6e-14
+    # Kasten & Young (1989): 1/M = sin(gamma) + 0.50572 (gamma + 6.07995)^-1.6364, gamma = asin(c) in degrees
+    c = np.concatenate([rng.uniform(0, 1, 600_000), rng.uniform(0, 0.05, 100_000), rng.uniform(0.93, 1.0, 100_000),
+                        np.arange(0, 129) / 128.0, (np.arange(0, 128) + 0.5) / 128.0, [0.9375, 0.93750001, 1.0, 0.0]])
+    cl = c.astype(L)
+    gamma = np.arcsin(cl) * (L(180) / L(np.pi)) if False else np.arcsin(cl) * L(180) / np.arccos(L(-1))
+    want = cl + L(0.50572) * (gamma + L(6.07995)) ** L(-1.6364)
+    got = call(lib, "mc_inv_air_mass", c).astype(L)
+    rel = np.abs(got - want) / want
+    assert rel.max() < 6e-14, rel.max()
+    assert rel[c > 0.05].max() < 4e-15, rel[c > 0.05].max()
+
+
 def test_seventh_root(lib):
     """x**(1/7) by one Householder step from a float32 seed: <= ~8 ulp with the seed's relative error up to 3e-6
     (MUFU lg2/ex2 deliver ~4e-7)."""

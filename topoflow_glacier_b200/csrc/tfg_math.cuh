@@ -13,9 +13,11 @@
 
 #if defined(__CUDACC__)
 #define TFG_HD __device__ __forceinline__
+#define TFG_DEVTAB static __device__ const   // piecewise-polynomial tables in global memory, read through L1 (__ldg)
 #else
 #define TFG_HD inline
 #define __constant__ static const
+#define TFG_DEVTAB static const
 #endif
 
 namespace tfg {
@@ -372,6 +374,75 @@ TFG_HD double stull_wet_bulb(double T, double RH) {
   const double a4 = u * fma(u2, fma(u2, fma(u2, fma(u2, kML.st_c9, kML.st_c7), kML.st_c5), kML.st_c3), 1.0);
   const double t4 = (kML.st_d * (RH * sqrt_pos(RH))) * a4;
   return (((T * a1) + atan_diff(T + RH, RH - kML.st_c)) + t4) - kML.st_f;
+}
+
+// ---- piecewise polynomials on uniform bins (tables kWetBulbTab / kAtanTab / kAirMassC / kAirMassS) --------------
+// Bin k = rint(S x) is found with the 2^52 * 1.5 rounding trick (as in exp_tab); the local variable u = S x - k lies
+// in [-1/2, 1/2].  A row holds the coefficients highest degree first; even and odd powers are two Horner chains.
+// The tables sit in global memory and are read with 128-bit read-only loads: they are ~14 KB, indexed almost
+// uniformly across a warp (cos Z) or by the few snowing lanes (wet bulb), and stay L1-resident -- the forcing stream
+// uses evict-first loads.
+TFG_HD void ld_pair(const double* p, double& a, double& b) {
+#if defined(__CUDA_ARCH__)
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  a = t.x; b = t.y;
+#else
+  a = p[0]; b = p[1];
+#endif
+}
+TFG_HD int bin_of(double x, double S, double& u) {
+  const double t = fma(x, S, 6755399441055744.0);
+  u = fma(x, S, -(t - 6755399441055744.0));
+  return lo32(t);
+}
+TFG_HD double poly7_row(const double* row, double u) {
+  double c0, c1, c2, c3, c4, c5, c6, c7;
+  ld_pair(row, c0, c1); ld_pair(row + 2, c2, c3); ld_pair(row + 4, c4, c5); ld_pair(row + 6, c6, c7);
+  const double u2 = u * u;
+  const double ev = fma(fma(fma(c1, u2, c3), u2, c5), u2, c7);
+  const double od = fma(fma(fma(c0, u2, c2), u2, c4), u2, c6);
+  return fma(od, u, ev);
+}
+TFG_HD double poly5_row(const double* row, double u) {
+  double c0, c1, c2, c3, c4, c5;
+  ld_pair(row, c0, c1); ld_pair(row + 2, c2, c3); ld_pair(row + 4, c4, c5);
+  const double u2 = u * u;
+  return fma(fma(fma(c0, u2, c2), u2, c4), u, fma(fma(c1, u2, c3), u2, c5));
+}
+
+// Stull (2011) wet bulb, table-driven, for 3/64 <= RH <= 2 and |T| <= 100 (see stull_wet_bulb for the formula):
+//   T_wb = T a1(RH) + atan(T + RH) + g(RH),  g = -atan(RH - 1.676331) + 0.00391838 RH^1.5 atan(0.023101 RH) - 4.86035
+// a1 and g from one table row, atan from the atan table after an argument inversion: ~40 FP64 instructions instead
+// of ~80 (no square root, no degree-20 arctangent).  Absolute error <= 3e-14 (tests/test_host_math.py).
+TFG_HD double stull_wet_bulb_tab(double T, double RH) {
+  double u;
+  const int k = bin_of(RH, 16.0, u);
+  const double* row = kWetBulbTab[k];
+  const double a1 = poly5_row(row, u);
+  const double g = poly7_row(row + 6, u);
+  const double x = T + RH, ax = fabs(x);
+  const bool inv = ax > 1.0;
+  const double t = inv ? rcp3(ax) : ax;
+  double v;
+  const int k2 = bin_of(t, 16.0, v);
+  double a = poly7_row(kAtanTab[k2], v);
+  a = inv ? ((kML.pio2h - a) + kML.pio2l) : a;
+  return fma(T, a1, g) + copysign(a, x);
+}
+
+// 1 / M for the Kasten & Young (1989) optical air mass M = 1/(sin g + 0.50572 (g + 6.07995)^-1.6364), g = asin(c) in
+// degrees, c = cos Z in [0, 1] (reference solar_funcs.py:540-568): replaces asin + log + exp of the closed form by one
+// table row (plus a square root above 70 deg elevation).  Relative error <= 6e-14 (5e-14 in the first bin above the
+// horizon, <= 3e-15 above 3 deg elevation; tests/test_host_math.py).
+TFG_HD double inv_air_mass(double c) {
+  double u;
+  if (c <= 0.9375) {
+    const int k = bin_of(c, 128.0, u);
+    return poly7_row(kAirMassC[k], u);
+  }
+  const double s = sqrt_pos(0.5 * (1.0 - fmin(c, 1.0)));
+  const int k = bin_of(s, 64.0, u);
+  return poly7_row(kAirMassS[k], u);
 }
 
 // ---- float32 counterparts (coefficients are FFMA immediates; MUFU reciprocal / rsqrt) ------------------------

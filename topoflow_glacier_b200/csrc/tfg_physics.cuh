@@ -17,6 +17,12 @@ struct LitTable {
 };
 static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.11, 17.3, 237.3, 0.611, 90.0, 0.50572, 6.07995, 1.6364, -1.6364, -0.1240, 0.0207, -0.0682, 0.0248, -0.0363, 0.0084, -0.0572, 0.0173, 257.14, 18.678, 1.12, 0.0614, 0.12, 0.05, 0.4, 0.44, 0.3, 0.15, 0.151977, 8.313659, 1.676331, 0.00391838, 0.023101, 4.86035, 273.15, 12.0, 0.03, 3600.0, 0.01, 0.1, 3.141592653589793};
 #define LIT(field, value) (P::f32 ? Num<P>(value) : Num<P>(static_cast<typename P::raw>(kLit.field)))
+#ifndef TFG_AIRMASS_TABLE   // fast float64: Kasten-Young air mass from the table of tfg_math.cuh (0: closed form, A/B runs)
+#define TFG_AIRMASS_TABLE 1
+#endif
+#ifndef TFG_WETBULB_TABLE   // fast float64: Stull wet bulb from the tables of tfg_math.cuh (0: closed form, A/B runs)
+#define TFG_WETBULB_TABLE 1
+#endif
 
 // host-precomputed scalars (products/ratios formed in the reference's own order)
 template <class raw>
@@ -170,11 +176,16 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   } else {
     // elevation angle gamma = 90deg - Z = asin(cos Z), sin(gamma) = cos Z; a/(gamma+b)^c = a*exp(-c*log(gamma+b))
     t1 = relu(cosZ);
-    const R elev_rad = nasin01(t1);
-    gamma = elev_rad * R(k.rad2deg);
-    t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(fmadd(elev_rad, R(k.rad2deg), LIT(ky_b, 6.07995))));
+    if constexpr (!TFG_AIRMASS_TABLE || !P::lean) {
+      const R elev_rad = nasin01(t1);
+      gamma = elev_rad * R(k.rad2deg);
+      t2 = LIT(ky_a, 0.50572) * nexp(LIT(ky_nc, -1.6364) * nlog(fmadd(elev_rad, R(k.rad2deg), LIT(ky_b, 6.07995))));
+    }
   }
-  const R M_opt = R(1.0) / (t1 + t2);
+  R M_opt;
+  // lean: 1/M = sin(gamma) + t2 as one piecewise polynomial in cos Z (fm::inv_air_mass): no asin, log, exp
+  if constexpr (TFG_AIRMASS_TABLE && P::lean) M_opt = R(fm::rcp3(fm::inv_air_mass(t1.v)));
+  else M_opt = R(1.0) / (t1 + t2);
   // Atmospheric_Transmissivity solar_funcs.py:608-614
   const R a_sa = fnmadd(LIT(sa_a1, 0.0207), W_p, LIT(sa_a0, -0.1240));
   const R b_sa = fnmadd(LIT(sa_b1, 0.0248), W_p, LIT(sa_b0, -0.0682));
@@ -392,9 +403,11 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
     R T_wb;
     bool stull_fast = false;
-    if constexpr (P::lean || P::f32) stull_fast = (RH >= 0.0) && (RH <= 2.0);
+    if constexpr (P::lean && TFG_WETBULB_TABLE) stull_fast = (RH >= 0.046875) && (RH <= 2.0);   // table bins 1..32
+    else if constexpr (P::lean || P::f32) stull_fast = (RH >= 0.0) && (RH <= 2.0);
     if (stull_fast) {
       if constexpr (P::f32) T_wb = R(fm::stull_wet_bulb32(T_air.v, RH.v));
+      else if constexpr (TFG_WETBULB_TABLE) T_wb = R(fm::stull_wet_bulb_tab(T_air.v, RH.v));
       else T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));
     } else {
       T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
