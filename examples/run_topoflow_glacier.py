@@ -1,15 +1,25 @@
-"""Thin counterpart of the reference's examples/run_topoflow_glacier.py (reference :10-123) on a B200.
+"""Counterpart of the reference's examples/run_topoflow_glacier.py (reference :10-131) on a B200.
 
-The reference example reads ``data/cat-3062920.csv`` (a large blob that is not part of the upstream checkout);
-here the 288 hourly rows of its test sample, already unit-converted, come from ``tests/golden/cats288.npz``.
-Two ways to drive the same model are shown:
+    python examples/run_topoflow_glacier.py [--config config/cat-3062920.yaml] [--forcing FILE.csv] [--const]
+                                            [--ensemble] [--mode f64|f64_fast|f32]
 
-1. the reference's per-step BMI loop (7 x set_value, update, get_value) -- one kernel launch per step;
-2. the fused path: all four shipped catchments as one ensemble, the whole window in ONE kernel launch.
+Like the reference driver it opens a catchment yaml, reads the forcing CSV the yaml names (``--forcing`` overrides it),
+keeps the rows inside ``start_time .. end_time``, converts units (mm/h -> m/h, K -> degC, wind = sqrt(U^2 + V^2)) and
+reports the final-step outputs and the routed hydrograph (the reference's 20-tap 0.05 box "mock routing", :129-131).
+``--const`` applies the overrides of run_topoflow_glacier_const.py:64-65 (RAINRATE := 3.0, T2D := 10 degC).
 
-    python examples/run_topoflow_glacier.py
+The same model is driven three ways:
+
+1. the reference's per-step BMI loop (7 x set_value, update(), 8 x get_value) -- one kernel launch per step;
+2. the streamed path: CSV -> pinned host block -> cudaMemcpyAsync -> device unit conversion -> fused launches
+   (``ForcingStreamer``), per-step hydrograph recorded on the device and routed there (``tfg_route_fir``);
+3. with ``--ensemble``: all catchment yamls of ``config/`` that share the window as ONE device-resident model.
+
+The upstream per-catchment CSVs are large blobs missing from the upstream checkout, so the shipped configs point at the
+one sample that exists (tests/data/sample-cat-3062920.csv, 288 hourly rows from 2013-03-20).
 """
 
+import argparse
 import sys
 import time
 from pathlib import Path
@@ -19,51 +29,113 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from topoflow_glacier import BmiTopoflowGlacier  # noqa: E402  (same import path as the reference)
+from topoflow_glacier import BmiTopoflowGlacier, configure_logging, logger  # noqa: E402  (the reference's import path)
+from topoflow_glacier_b200.forcing import ForcingStreamer, convert_on_host, read_forcing_csv  # noqa: E402
+from topoflow_glacier_b200.timebase import parse_start  # noqa: E402
 
 INPUTS = ("atmosphere_water__liquid_equivalent_precipitation_rate", "land_surface_air__temperature",
           "land_surface_air__pressure", "atmosphere_air_water~vapor__relative_saturation", "wind_speed_UV")
 
 
-def main():
+def load_raw(model, forcing_path, const: bool) -> np.ndarray:
+    """``[T, 6]`` raw met columns inside the configured window (reference :30-38), optional const overrides."""
+    start, end = parse_start(model.cfg.start_time), parse_start(model.cfg.end_time)
+    raw = read_forcing_csv(forcing_path, start, end)
+    if const:  # run_topoflow_glacier_const.py:64-65
+        raw[:, 0] = 3.0
+        raw[:, 1] = 10.0 - model.K_to_C
+    return raw
+
+
+def run(config: Path, forcing: Path | None, const: bool, mode: str, ensemble: bool) -> dict:
     import torch
+    import yaml
 
-    z = np.load(ROOT / "tests" / "golden" / "cats288.npz")
-    forcing = z["forcing"]  # [288, 5, 4]: P [m/h], T_air [degC], P_air [Pa], Hum_sp, uz
-    keys = ("da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice", "h0_swe", "h0_iwe", "T_rain_snow")
-    cfgs = [dict({k: float(z[f"static_{k}"][i]) for k in keys}, site_prefix=f"cat-{i}", forcing_file="-", dt=1,
-                 start_time="2013032000", end_time="2013033123") for i in range(4)]
-
-    # 1. per-step BMI loop, catchment 1 (cat-3062920)
+    configure_logging()
+    with open(config) as f:
+        cfg = yaml.safe_load(f)
+    cfg["precision"] = mode
     model = BmiTopoflowGlacier()
-    model.initialize_ensemble([cfgs[1]])
-    runoff = np.zeros(len(forcing))
+    model.initialize_ensemble([cfg])
+    forcing_path = Path(forcing) if forcing else (ROOT / model.cfg.forcing_file)
+    raw = load_raw(model, forcing_path, const)
+    live = convert_on_host(raw[:, :, None])[:, :, 0]          # [T, 5]: the driver-side unit conversions
+    T = live.shape[0]
+    logger.info(f"{config.name}: {T} forcing rows from {forcing_path}")
+
+    # 1. the reference's per-step loop
+    dest = np.zeros(1)
+    print(f"|- Starting Snow Height: {model.get_value('snowpack__depth', dest).item()}")
+    print(f"|- Starting Ice Height: {model.get_value('glacier_ice__thickness', dest).item()}")
+    runoff = np.zeros(T)
     t0 = time.perf_counter()
-    for i in range(len(forcing)):
-        for name, v in zip(INPUTS, forcing[i, :, 1]):
+    for i in range(T):
+        for name, v in zip(INPUTS, live[i]):
             model.set_value(name, v)
         model.update()
         runoff[i] = model.get_value("land_surface_water__runoff_volume_flux", np.zeros(1))[0]
     dt_loop = time.perf_counter() - t0
-    runoff *= model.da_m2  # m/s -> m3/s, as the reference driver does (:115)
-    print(f"per-step BMI loop : {len(forcing)} steps in {dt_loop * 1e3:.1f} ms, total runoff {runoff.sum():.4f} m3/s-steps")
-    for name in model.get_output_var_names():
-        print(f"   {name:60s} {model.get_value(name, np.zeros(1))[0]:.6g} {model.get_var_units(name)}")
+    final = {name: float(model.get_value(name, np.zeros(1))[0]) for name in model.get_output_var_names()}
+    runoff *= model.da_m2                                      # m/s -> m3/s (:115)
+    routed = np.convolve(runoff, np.zeros(20) + 0.05, mode="full")[:T]   # :129-131
+    for name, v in final.items():
+        print(f"|- Final Timestep {name}: {v:.9g} {model.get_var_units(name)}")
+    print(f"per-step BMI loop : {T} steps in {dt_loop * 1e3:.1f} ms ({dt_loop / T * 1e6:.0f} us/step); "
+          f"runoff sum {runoff.sum():.6f} m3/s-steps, routed peak {routed.max():.6f} m3/s")
     model.finalize()
 
-    # 2. ensemble of the four catchments, fused
-    ens = BmiTopoflowGlacier()
-    ens.initialize_ensemble(cfgs)
-    dev = torch.as_tensor(forcing).cuda()
+    # 2. streamed + fused: host block -> side-stream H2D -> device conversion -> fused launches, routing on the device
+    fused = BmiTopoflowGlacier()
+    fused.initialize_ensemble([cfg])
+    eng = fused._engine
+    streamer = ForcingStreamer(eng, chunk_steps=128, raw_dtype="float64")
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    series = ens.update_steps(len(forcing), dev, record=("M_total",))
+    parts = [eng.run(chunk, chunk.shape[0], record=("M_total",))["M_total"] for chunk in streamer.chunks(raw[:, :, None])]
+    q_dev = torch.cat(parts).to(torch.float64) * torch.as_tensor(np.atleast_1d(fused.da_m2), device=eng.device)
+    routed_dev = eng.route_fir(q_dev)
     torch.cuda.synchronize()
     dt_fused = time.perf_counter() - t0
-    q = series["M_total"].cpu().numpy() * ens.da_m2[None, :]
-    print(f"fused ensemble    : 4 catchments x {len(forcing)} steps in {dt_fused * 1e3:.2f} ms; "
-          f"catchment 1 total {q[:, 1].sum():.4f} (same as above: {np.allclose(q[:, 1], runoff, rtol=1e-12)})")
-    ens.finalize()
+    q = q_dev.cpu().numpy()[:, 0]
+    same = bool(np.array_equal(q, runoff)) if mode == "f64" else bool(np.allclose(q, runoff, rtol=1e-9, atol=1e-12))
+    print(f"streamed + fused  : {T} steps in {dt_fused * 1e3:.2f} ms; hydrograph equals the per-step loop: {same}; "
+          f"routed peak {float(routed_dev.max()):.6f} m3/s")
+    fused.finalize()
+    out = {"runoff_m3s": runoff, "routed_m3s": routed, "final": final, "fused_runoff_m3s": q,
+           "fused_routed_m3s": routed_dev.cpu().numpy()[:, 0]}
+
+    # 3. every shipped catchment with the same window as one ensemble, one forcing series each (here: the same sample)
+    if ensemble:
+        cfgs = []
+        for p in sorted((ROOT / "config").glob("cat-*.yaml")):
+            c = yaml.safe_load(open(p))
+            if (str(c["start_time"]), c["dt"]) == (str(cfg["start_time"]), cfg["dt"]):
+                cfgs.append(dict(c, precision=mode))
+        ens = BmiTopoflowGlacier()
+        ens.initialize_ensemble(cfgs)
+        block = torch.as_tensor(np.repeat(live[:, :, None], len(cfgs), axis=2)).to(ens._engine.device, ens._engine.dtype)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        series = ens.update_steps(T, block.contiguous(), record=("M_total",))
+        torch.cuda.synchronize()
+        dt_e = time.perf_counter() - t0
+        qe = series["M_total"].cpu().numpy() * np.atleast_1d(ens.da_m2)[None, :]
+        print(f"fused ensemble    : {len(cfgs)} catchments x {T} steps in {dt_e * 1e3:.2f} ms; runoff sums "
+              + ", ".join(f"{x:.4f}" for x in qe.sum(axis=0)))
+        ens.finalize()
+        out["ensemble_runoff_m3s"] = qe
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default=str(ROOT / "config" / "cat-3062920.yaml"))
+    ap.add_argument("--forcing", default=None, help="forcing CSV (default: the yaml's forcing_file, relative to the repository)")
+    ap.add_argument("--const", action="store_true", help="overrides of run_topoflow_glacier_const.py: RAINRATE = 3, T2D = 10 degC")
+    ap.add_argument("--ensemble", action="store_true", help="also run all shipped catchments of the same window as one model")
+    ap.add_argument("--mode", default="f64", choices=["f64", "f64_fast", "f32"])
+    a = ap.parse_args()
+    run(Path(a.config), a.forcing, a.const, a.mode, a.ensemble)
 
 
 if __name__ == "__main__":

@@ -187,6 +187,13 @@ TFG_API int tfg_ingest_async(tfg_ctx* ctx, const void* pinned_src, void* dev_dst
  *   P = RAINRATE*1e-3, T_air = -273.15 + T2D, P_air, Hum_sp, uz = sqrt(U2D^2 + V2D^2)             */
 TFG_API int tfg_convert_forcing(tfg_ctx* ctx, const void* raw, int raw_elem_size, void* out, int64_t n_steps,
                                 int64_t n_cells, void* stream);
+/* the same from PACKED columns, as NetCDF met archives store them (scale_factor / add_offset per variable, e.g. the
+ * NWM / AORC forcing files behind the per-catchment CSVs of examples/run_topoflow_glacier.py:30-49): raw dev int16
+ * [n_steps][6][n_cells]; value = (double)raw * scale[v] + offset[v] (two IEEE operations, so a host statement
+ * raw * scale + offset in float64 gives the same bits), then the unit conversions above.  12 bytes per cell-step cross
+ * PCIe instead of 24 (float32) or 48 (float64).  scale / offset are HOST arrays of 6 doubles.                      */
+TFG_API int tfg_convert_forcing_packed(tfg_ctx* ctx, const int16_t* raw, const double* scale, const double* offset, void* out,
+                                       int64_t n_steps, int64_t n_cells, void* stream);
 /* wait (device-side) on `stream` for an event recorded by tfg_ingest_async on another stream     */
 TFG_API int tfg_stream_wait_event(tfg_ctx* ctx, void* stream, void* event);
 

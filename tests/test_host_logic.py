@@ -115,6 +115,33 @@ def test_forcing_csv_header_keyed_and_windowed(tmp_path):
         read_forcing_csv(a)
 
 
+def test_shipped_forcing_samples_and_configs():
+    """The committed data fixtures (scripts/import_reference_data.py): both forcing samples of the reference parse by
+    header name although their columns come in different orders; all five catchment yamls validate (three hold integer
+    times the reference's own schema rejects) and name a forcing file that exists."""
+    import yaml
+
+    from topoflow_glacier_b200.config import TopoflowGlacierConfig
+    from topoflow_glacier_b200.forcing import RAW_COLUMNS, read_forcing_csv
+    from topoflow_glacier_b200.timebase import parse_start
+
+    a = read_forcing_csv(ROOT / "tests" / "data" / "sample-cat-3062920.csv")
+    b = read_forcing_csv(ROOT / "tests" / "data" / "mock-forcing-june2012.csv")
+    assert a.shape == (288, 6) and b.shape == (168, 6)
+    assert a[0, RAW_COLUMNS.index("PSFC")] == 88313.5625 and a[0, RAW_COLUMNS.index("T2D")] == 275.2267761230469
+    assert b[0, RAW_COLUMNS.index("PSFC")] == 99472.1 and b[0, RAW_COLUMNS.index("T2D")] == 290.82
+    assert b[0, RAW_COLUMNS.index("U2D")] == 0.681 and b[0, RAW_COLUMNS.index("V2D")] == -3.783
+    names = sorted(p.name for p in (ROOT / "config").glob("cat-*.yaml"))
+    assert names == ["cat-3062784.yaml", "cat-3062920-const.yaml", "cat-3062920.yaml", "cat-3062924.yaml", "cat-3062927.yaml"]
+    for n in names:
+        raw = yaml.safe_load(open(ROOT / "config" / n))
+        cfg = TopoflowGlacierConfig.model_validate(raw)
+        assert isinstance(cfg.start_time, str) and (ROOT / cfg.forcing_file).exists() and cfg.tz_name == "America/Los_Angeles"
+        window = read_forcing_csv(ROOT / cfg.forcing_file, parse_start(cfg.start_time), parse_start(cfg.end_time))
+        assert window.shape[0] == 288   # the sample ends 2013-03-31 23:00; every shipped window contains it
+    assert isinstance(yaml.safe_load(open(ROOT / "config" / "cat-3062784.yaml"))["start_time"], int)
+
+
 def test_shard_bounds_cover_all_cells():
     from topoflow_glacier_b200.sharding import shard_bounds, shard_sizes
 

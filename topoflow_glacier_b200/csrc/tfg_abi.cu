@@ -170,6 +170,26 @@ __global__ void convert_kernel(const src_t* __restrict__ in, raw* __restrict__ o
   }
 }
 
+struct PackScale { double scale[6], offset[6]; };
+template <class raw>
+__global__ void convert_packed_kernel(const int16_t* __restrict__ in, raw* __restrict__ out, int64_t n_steps, int64_t N,
+                                      const PackScale ps) {
+  const int64_t total = n_steps * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / N, c = i - t * N;
+    const int16_t* r = in + t * 6 * N + c;
+    double v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v[j] = __dadd_rn(__dmul_rn((double)__ldcs(r + j * N), ps.scale[j]), ps.offset[j]);
+    raw* o = out + t * TFG_N_FORCING * N + c;
+    o[0] = (raw)__dmul_rn(v[0], 0.001);
+    o[N] = (raw)__dadd_rn(-273.15, v[1]);
+    o[2 * N] = (raw)v[2];
+    o[3 * N] = (raw)v[3];
+    o[4 * N] = (raw)__dsqrt_rn(__dadd_rn(__dmul_rn(v[4], v[4]), __dmul_rn(v[5], v[5])));
+  }
+}
+
 // ---- causal box/FIR filter along time: the "mock routing" of the reference example --------------------------
 // out[t][j] = sum_{k < taps} w[k] * in[t-k][j]   (np.convolve(x, w, "full")[:T], examples/run_topoflow_glacier.py:129-131)
 __global__ void fir_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ w,
@@ -425,6 +445,22 @@ int tfg_convert_forcing(tfg_ctx* x, const void* raw, int raw_elem_size, void* ou
     if (f32out) convert_kernel<float, float><<<grid, 256, 0, s>>>(r, static_cast<float*>(out), n_steps, n_cells);
     else convert_kernel<float, double><<<grid, 256, 0, s>>>(r, static_cast<double*>(out), n_steps, n_cells);
   }
+  TFG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tfg_convert_forcing_packed(tfg_ctx* x, const int16_t* raw, const double* scale, const double* offset, void* out,
+                               int64_t n_steps, int64_t n_cells, void* stream) {
+  if (!x || !raw || !out || !scale || !offset) return fail("tfg_convert_forcing_packed: NULL argument");
+  if (n_steps <= 0 || n_cells <= 0) return fail("tfg_convert_forcing_packed: empty block");
+  TFG_CUDA(cudaSetDevice(x->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PackScale ps;
+  for (int j = 0; j < 6; ++j) { ps.scale[j] = scale[j]; ps.offset[j] = offset[j]; }
+  const int64_t total = n_steps * n_cells;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  if (x->mode == TFG_F32) convert_packed_kernel<float><<<grid, 256, 0, s>>>(raw, static_cast<float*>(out), n_steps, n_cells, ps);
+  else convert_packed_kernel<double><<<grid, 256, 0, s>>>(raw, static_cast<double*>(out), n_steps, n_cells, ps);
   TFG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -245,6 +245,18 @@ class MeltEngine:
         self.step_index += T
         return {k: rec_t[:, i] for i, k in enumerate(names)} if rec_t is not None else {}
 
+    def snapshot_outputs(self, names: Sequence[str], dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``[len(names), N]`` device copy of the named state rows, cast to ``dtype`` (e.g. ``torch.float32`` to halve the
+        device->host traffic of a hydrograph product); ``out`` (pinned host tensor) receives it asynchronously on the
+        current stream -- synchronise the stream (or record an event) before reading it."""
+        rows = torch.tensor([STATE_ROWS.index(k) for k in names], device=self.device)
+        snap = self.state.index_select(0, rows)
+        if dtype is not None and dtype != snap.dtype:
+            snap = snap.to(dtype)
+        if out is not None:
+            out.copy_(snap, non_blocking=True)
+        return snap
+
     def set_forcing_map(self, forcing_index, n_forcing_cols: Optional[int] = None, _alloc_inputs: bool = True):
         """(Re)bind the cell -> forcing-column map (``None`` restores one column per cell); the input block of the
         per-step path is re-allocated with one column per forcing column."""

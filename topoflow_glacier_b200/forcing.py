@@ -22,7 +22,8 @@ from typing import Iterator, Optional, Sequence
 import numpy as np
 import pandas as pd
 
-__all__ = ["RAW_COLUMNS", "read_forcing_csv", "stack_catchments", "convert_on_host", "ForcingStreamer"]
+__all__ = ["RAW_COLUMNS", "read_forcing_csv", "stack_catchments", "convert_on_host", "ForcingStreamer",
+           "DEFAULT_PACKING", "pack_forcing", "unpack_forcing", "bind_host_to_gpu"]
 
 # raw met columns moved to the device, in kernel order (tfg_convert_forcing)
 RAW_COLUMNS = ("RAINRATE", "T2D", "PSFC", "Q2D", "U2D", "V2D")
@@ -63,10 +64,48 @@ def convert_on_host(raw: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(np.stack([rain * 10 ** (-3), -273.15 + t2d, psfc, q2d, (u**2 + v**2) ** 0.5], axis=1))
 
 
-class ForcingStreamer:
-    """Double-buffered host -> device forcing pipeline for one ``MeltEngine``."""
+# NetCDF-style packing of the six raw columns (value = int16 * scale + offset), wide enough for any met record:
+# RAINRATE 0..163 mm/h in 0.005 steps, T2D 109..437 K in 0.005 K, PSFC 34 464..165 536 Pa in 2 Pa, Q2D 0..0.065 in
+# 1e-6, U2D / V2D +-163 m/s in 0.005.  (scale, offset) per column of RAW_COLUMNS.
+DEFAULT_PACKING = (np.array([0.005, 0.005, 2.0, 1e-6, 0.005, 0.005]), np.array([163.84, 273.15, 100000.0, 0.0325, 0.0, 0.0]))
 
-    def __init__(self, engine, chunk_steps: int, n_buffers: int = 2, raw_dtype="float64"):
+
+def pack_forcing(raw: np.ndarray, packing=DEFAULT_PACKING) -> np.ndarray:
+    """``[T, 6, N]`` float raw columns -> int16 (round to nearest, saturating)."""
+    scale, offset = (np.asarray(a, dtype=np.float64).reshape(1, 6, 1) for a in packing)
+    q = np.rint((np.asarray(raw, dtype=np.float64) - offset) / scale)
+    return np.ascontiguousarray(np.clip(q, -32768, 32767).astype(np.int16))
+
+
+def unpack_forcing(packed: np.ndarray, packing=DEFAULT_PACKING) -> np.ndarray:
+    """Host statement of what the device computes from packed columns: ``int16 * scale + offset`` in float64."""
+    scale, offset = (np.asarray(a, dtype=np.float64).reshape(1, 6, 1) for a in packing)
+    return packed.astype(np.float64) * scale + offset
+
+
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores next to GPU ``device_index`` (NVML's ideal affinity), so that pinned
+    staging buffers allocated afterwards are first-touched on that GPU's NUMA node.  With several ranks streaming
+    forcing at once the host->device copies otherwise cross the socket interconnect.  Returns False when NVML (or
+    the permission to change the affinity) is missing."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
+class ForcingStreamer:
+    """Double-buffered host -> device forcing pipeline for one ``MeltEngine``.
+
+    ``raw_dtype``: ``"float64"`` / ``"float32"`` raw columns, or ``"int16"`` for packed columns (``packing=(scale,
+    offset)``, default ``DEFAULT_PACKING``; see ``pack_forcing``) -- 12 instead of 24 / 48 bytes per cell-step over PCIe."""
+
+    def __init__(self, engine, chunk_steps: int, n_buffers: int = 2, raw_dtype="float64", packing=None):
         import torch
 
         from . import _lib
@@ -80,8 +119,15 @@ class ForcingStreamer:
         N, dev = engine.n_cols, engine.device   # forcing columns (= cells unless the engine has a forcing map)
         self.N = N
         self.side = torch.cuda.Stream(device=dev)
-        self.raw_dtype = torch.float32 if str(raw_dtype).endswith("32") else torch.float64
-        self.raw_es = 4 if self.raw_dtype == torch.float32 else 8
+        name = str(raw_dtype)
+        self.raw_dtype = torch.int16 if name.endswith("int16") else torch.float32 if name.endswith("32") else torch.float64
+        self.raw_es = {torch.int16: 2, torch.float32: 4, torch.float64: 8}[self.raw_dtype]
+        self.packing = None
+        if self.raw_dtype == torch.int16:
+            sc, of = packing if packing is not None else DEFAULT_PACKING
+            self.packing = (np.ascontiguousarray(sc, dtype=np.float64), np.ascontiguousarray(of, dtype=np.float64))
+            if self.packing[0].shape != (6,) or self.packing[1].shape != (6,):
+                raise ValueError("packing must be (scale[6], offset[6])")
         self.pinned = [None] * self.nb  # staging for NumPy sources, allocated on first use
         self.d_raw = [torch.empty(self.Tc, 6, N, dtype=self.raw_dtype, device=dev) for _ in range(self.nb)]
         self.d_out = [torch.empty(self.Tc, 5, N, dtype=engine.dtype, device=dev) for _ in range(self.nb)]
@@ -113,8 +159,13 @@ class ForcingStreamer:
             self._lib.check(lib.tfg_ingest_async(e.ctx, src_ptr, self.d_raw[b].data_ptr(), nbytes,
                                                  self.side.cuda_stream, None), "tfg_ingest_async")
             self.h2d_done[b].record(self.side)
-            self._lib.check(lib.tfg_convert_forcing(e.ctx, self.d_raw[b].data_ptr(), self.raw_es, self.d_out[b].data_ptr(), Tk, self.N,
-                                                    self.side.cuda_stream), "tfg_convert_forcing")
+            if self.packing is not None:
+                self._lib.check(lib.tfg_convert_forcing_packed(e.ctx, self.d_raw[b].data_ptr(), self.packing[0].ctypes.data,
+                                                               self.packing[1].ctypes.data, self.d_out[b].data_ptr(), Tk, self.N,
+                                                               self.side.cuda_stream), "tfg_convert_forcing_packed")
+            else:
+                self._lib.check(lib.tfg_convert_forcing(e.ctx, self.d_raw[b].data_ptr(), self.raw_es, self.d_out[b].data_ptr(), Tk,
+                                                        self.N, self.side.cuda_stream), "tfg_convert_forcing")
             self.ready[b].record(self.side)
         self.h2d_bytes += nbytes
         return Tk
