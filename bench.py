@@ -613,6 +613,7 @@ def run_gpu_arm(args):
         blk = forcing[:Ts, :, :N_BASIN].to(torch.float64)
         raw_cols.copy_(torch.stack([blk[:, 0] * 1e3, blk[:, 1] + 273.15, blk[:, 2], blk[:, 3], blk[:, 4] * 0.6,
                                     blk[:, 4] * 0.8], dim=1).to(torch.float32))
+        del blk   # a view: it would keep the whole forcing chunk alive
         streamer2 = ForcingStreamer(eng, Ts, raw_dtype="float32")
         agg_s = [BasinAggregates(Ts, N_BASIN, device=dev, exponents=agg_exps) for _ in range(2)]
         agg_sh = [torch.empty(Ts, N_BASIN, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
@@ -629,9 +630,9 @@ def run_gpu_arm(args):
     # sub-records: the other arithmetic modes (N == 1) and the strong-scaling regional grid (every N)
     # =================================================================================================================
     def free_headline():
-        nonlocal eng, forcing, agg, agg_e, out_host
+        nonlocal eng, forcing, agg, agg_e, out_host, elev, basin_id, zero_agg, reduce_agg, snap_probe
         eng.close()
-        eng = forcing = agg = agg_e = out_host = None
+        eng = forcing = agg = agg_e = out_host = elev = basin_id = zero_agg = reduce_agg = snap_probe = None
         import gc
 
         gc.collect()

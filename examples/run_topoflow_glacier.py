@@ -108,6 +108,8 @@ def run(config: Path, forcing: Path | None, const: bool, mode: str, ensemble: bo
     if ensemble:
         cfgs = []
         for p in sorted((ROOT / "config").glob("cat-*.yaml")):
+            if p.stem.endswith("-const"):   # the constant-forcing variant of cat-3062920 is a different experiment
+                continue
             c = yaml.safe_load(open(p))
             if (str(c["start_time"]), c["dt"]) == (str(cfg["start_time"]), cfg["dt"]):
                 cfgs.append(dict(c, precision=mode))

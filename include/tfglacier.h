@@ -150,6 +150,11 @@ TFG_API int tfg_bind_state(tfg_ctx* ctx, const tfg_state* s);
  * 0.03 m threshold (bmi_topoflow_glacier.py:1040), so decisions -- and hence all state -- are unchanged.  Set the third
  * row to NaN after changing the window from outside.  NULL switches it off.                                        */
 TFG_API int tfg_bind_window_carry(tfg_ctx* ctx, void* carry);
+/* float32 mode only, optional [2][n_cells] float scratch (zero it first): the low parts of h_swe / h_iwe.  With it the
+ * water-equivalent balances (bmi_topoflow_glacier.py:1594-1617) are carried as float + float and evaluated in float64
+ * inside the float32 kernel, so that the hour a pack melts out does not drift with float32 accumulation.  NULL = plain
+ * float32 balances.                                                                                                   */
+TFG_API int tfg_bind_mass_residual(tfg_ctx* ctx, void* lo);
 /* Optional forcing map: cell i reads column forcing_col[i] (dev int32 [n_cells], values in [0, n_cols)) of forcing
  * blocks that are then [n_steps][5][n_cols] -- the cells of one catchment share the catchment's forcing series, as the
  * reference's one-CSV-per-catchment drivers do (examples/run_topoflow_glacier.py:30-49), without replicating it per

@@ -11,16 +11,21 @@ STATIC_KEYS = ["da", "slope", "aspect", "lon", "lat", "elev", "h0_snow", "h0_ice
 CASES = ["sample265", "cats288", "const", "allconst", "nosnow", "rand64", "satterlund", "dt2", "year4",
          "cfgspace", "south_dt3", "polar", "dt24", "year2070"]
 
-# |gpu - ref| <= rtol*|ref| + atol, float64 modes (the atol of a flux is ~1e-12 x the size of
-# the terms that cancel in it, see DESIGN.md "Tolerances")
+# |gpu - ref| <= rtol*|ref| + atol, float64 modes.  rtol and atol are SURVEY.md 8a's table; the three departures from
+# it are marked and explained in DESIGN.md section 6 together with the worst error achieved per quantity
+# (profiles/r2_parity.csv): a relative bound is meaningless where the reference value itself passes through zero.
 RTOL = 1e-12
 ATOL = {
     "p0": 0, "e_sat_air": 0, "e_air": 0, "RH": 0, "e_sat_surf": 0, "W_p": 0, "Dn": 0, "em_air": 0, "albedo": 0,
-    "n": 0, "snow3day": 1e-13, "P_rain": 0, "P_snow": 0, "TSN_offset": 1e-14,
-    "T_dew": 1e-12, "T_surf": 1e-12, "Ri": 1e-13, "Dh": 1e-15, "e_surf": 0,
-    "Qh": 1e-10, "Qe": 1e-10, "Qn_SW": 1e-10, "Qn_LW": 1e-10, "Q_sum": 1e-9,
+    "n": 0, "P_rain": 0, "P_snow": 0, "TSN_offset": 0, "Ri": 0, "Dh": 0, "e_surf": 0,
+    "T_dew": 1e-13, "T_surf": 1e-13,      # departure 1: degC values cross 0 (survey: 0); worst achieved 1.2e-14 K
+    "Qh": 1e-12, "Qe": 1e-12, "Qn_LW": 1e-12,
+    "Qn_SW": 1e-11,                       # departure 2: cos Z cancels at the horizon (survey: 1e-12); worst 3.9e-12 W m-2
+    "Q_sum": 1e-9,
     "SM": 3e-18, "IM": 3e-18, "M_total": 3e-18,
-    "h_swe": 1e-14, "h_iwe": 1e-13, "h_snow": 2e-13, "h_ice": 1e-13, "Eccs": 1e-5, "Ecci": 1e-5,
+    "h_swe": 1e-15, "h_iwe": 1e-15, "h_snow": 1e-15, "h_ice": 1e-15, "Eccs": 1e-6, "Ecci": 1e-6,
+    # not in the survey's table: the running window sum (exact only inside its guard band, by design) and the integrals
+    "snow3day": 1e-13,                    # departure 3: incremental sum of 72 entries ~1e-3 m; decisions (n) are exact
     "vol_P": 1e-9, "vol_PR": 1e-9, "vol_PS": 1e-9, "vol_SM": 1e-6, "vol_IM": 1e-6, "P_max": 0,
 }
 

@@ -138,42 +138,47 @@ def test_kernel_instantiations_agree_bit_for_bit(mode, cuda_device):
         e.close()
 
 
-def test_f32_mode_tolerance(cuda_device):
-    """fp32 mode has its own, looser, stated tolerance (DESIGN.md "fp32 mode").
+F32_TOL = {"Qn_SW": (2e-3, 0.05), "Qn_LW": (2e-3, 0.05), "Qh": (2e-3, 0.05), "Qe": (2e-3, 0.05), "Q_sum": (2e-3, 0.2),
+           "RH": (1e-4, 0), "albedo": (1e-5, 0), "T_surf": (1e-4, 1e-3), "SM": (2e-3, 2e-10), "IM": (2e-3, 2e-10),
+           "M_total": (2e-3, 2e-10), "h_swe": (1e-4, 1e-6), "h_iwe": (1e-4, 1e-6), "h_snow": (1e-4, 2e-5), "h_ice": (1e-4, 2e-6)}
 
-    float32 moves the melt-out knife edges (helpers.knife_edge_mask) much more often than a 1-ulp float64
-    difference does, so surface-type transitions may shift by a step or two.  Stated bound: on cell-steps where
-    the surface class (snow / bare-or-ice) agrees with the oracle and no transition is within 3 steps, fluxes
-    agree to 2e-3 relative + 0.05 W m-2; those cell-steps are >= 90 % of all; depths agree to 1 %.
-    """
+
+@pytest.mark.parametrize("name", ["cats288", "rand64", "cfgspace"])
+def test_f32_mode_tolerance(name, cuda_device):
+    """fp32 mode has its own, looser, stated tolerance (DESIGN.md "fp32 mode"), on ALL cell-steps.
+
+    The water-equivalent balances run in float64 inside the float32 kernel (tfg_bind_mass_residual), so the hour a
+    pack melts out no longer drifts with float32 accumulation and no "calm" filter is needed any more.  Stated bound:
+    fluxes 2e-3 relative + 0.05 W m-2 (Q_sum 0.2 W m-2: it is a difference of ~300 W m-2 terms), melt rates 2e-3 + 2e-10
+    m/s, depths 1e-4 relative + 1e-6 m, on every cell-step except cells past a melt-out knife edge
+    (helpers.knife_edge_mask: a residue of ~1e-8 of the pack that one side keeps and the other does not), whose number
+    is bounded."""
     import torch
 
-    case, want = oracle_series("cats288")
+    from helpers import knife_edge_mask
+
+    case, want = oracle_series(name)
     eng = make_engine(case, mode="f32")
     forcing = torch.as_tensor(case["forcing"]).to(cuda_device, torch.float32)
     got = {k: v.cpu().numpy().astype(np.float64) for k, v in eng.run(forcing, record=REC).items()}
-    same = (got["h_snow"] > 0) == (want["h_snow"] > 0)
-    calm = same.copy()
-    for sh in range(1, 4):  # no class disagreement within +-3 steps
-        calm[sh:] &= same[:-sh]
-        calm[:-sh] &= same[sh:]
-    rep = {"calm_fraction": float(calm.mean())}
-    tol = {"Qn_SW": (2e-3, 0.05), "Qn_LW": (2e-3, 0.05), "Qh": (2e-3, 0.05), "Qe": (2e-3, 0.05), "Q_sum": (2e-3, 0.2),
-           "RH": (1e-4, 0), "albedo": (1e-5, 0), "T_surf": (1e-4, 1e-3)}
-    bad = []
-    for k, (rt, at) in tol.items():
-        ok, ratio, dabs, drel = err_report(got[k][calm], want[k][calm], at, rt)
-        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
-        if not ok:
-            bad.append((k, ratio, dabs, drel))
-    for k in ("h_swe", "h_iwe"):
-        ok, ratio, dabs, drel = err_report(got[k][-1], want[k][-1], 1e-4, 1e-2)
-        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
-        if not ok:
-            bad.append((k, ratio, dabs, drel))
-    _dump("cats288/f32", rep)
     eng.close()
-    assert calm.mean() >= 0.90, calm.mean()
+    # float32 residues are ~1e-8 of the pack, not 1e-17: same detector, float32 threshold
+    T, N = want["h_swe"].shape
+    mask = np.zeros((T, N), dtype=bool)
+    for key in ("h_swe", "h_iwe"):
+        g, w = got[key], want[key]
+        prev = np.vstack([np.full((1, N), np.inf), np.maximum(np.abs(w[:-1]), np.abs(g[:-1]))])
+        residue = ((g == 0) != (w == 0)) & (np.maximum(np.abs(g), np.abs(w)) <= 1e-5 * np.maximum(prev, 1e-6))
+        mask |= np.maximum.accumulate(residue, axis=0)
+    rep = {"knife_edge_cells": int(mask[-1].sum()), "cells": N, "steps": T}
+    bad = []
+    for k, (rt, at) in F32_TOL.items():
+        ok, ratio, dabs, drel = err_report(got[k][~mask], want[k][~mask], at, rt)
+        rep[k] = {"ok": ok, "err_over_tol": ratio, "max_abs": dabs, "max_rel": drel}
+        if not ok:
+            bad.append((k, ratio, dabs, drel))
+    _dump(f"{name}/f32", rep)
+    assert mask[-1].sum() <= max(1, 0.1 * N), rep
     assert not bad, bad
 
 
@@ -207,11 +212,18 @@ def test_large_random_sample_with_knife_edges(mode, cuda_device):
     got = {k: v.cpu().numpy() for k, v in eng.run(torch.as_tensor(forcing).to(cuda_device), record=keys).items()}
     eng.close()
     mask = knife_edge_mask(got, want)
-    # the log-law drag coefficient kappa/log((z - h_snow)/z0) (reference :670) is singular at h_snow = z - z0 =
-    # 9.99 m: within a few cm of it a 1-ulp change of h_snow moves Qh/Qe by >1e-12 relative in ANY implementation
-    hs = np.vstack([statics["h0_snow"][None, :], want["h_snow"]])
-    singular = ((hs > 9.9) & (hs < 10.0)).any(axis=0)
-    mask |= singular[None, :]
+    # The log-law drag coefficient kappa/ln((z - h_snow)/z0) (reference :670) is singular at h_snow = z - z0 = 9.99 m.
+    # Condition number of Dn with respect to h_snow: |d ln Dn / d ln h| = 2 h / ((z - h) |ln((z - h)/z0)|) (0 once the
+    # argument is clamped at 0.01).  h_snow carries a few ulp (~5e-16 relative) of legitimate difference between two
+    # libms, so a 1e-12 bound on the fluxes is only meaningful where cond * 5e-16 < 1e-12 / 4, i.e. cond < 500: such a
+    # cell is masked from the step it enters that zone (its state is contaminated afterwards), and counted.
+    hs = np.vstack([statics["h0_snow"][None, :], want["h_snow"][:-1]])      # depth the step STARTS from
+    arg = (10.0 - hs) / 0.01
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cond = np.where(arg > 0.01, 2.0 * hs / (np.abs(10.0 - hs) * np.abs(np.log(np.maximum(arg, 1e-300)))), 0.0)
+    singular = np.maximum.accumulate(np.nan_to_num(cond, posinf=np.inf) > 500.0, axis=0)
+    mask |= singular
+    singular = singular[-1]
     melted = int(((want["h_swe"][0] > 0) & (want["h_swe"][-1] == 0)).sum())
     rep = {"cells": N, "steps": T, "cells_melted_out": melted, "knife_edge_cells": int(mask[-1].sum() - singular.sum()),
            "log_law_singular_cells": int(singular.sum())}
@@ -223,7 +235,7 @@ def test_large_random_sample_with_knife_edges(mode, cuda_device):
             bad.append((k, ratio, dabs, drel))
     _dump(f"random16k/{mode}", rep)
     assert melted > 100
-    assert rep["knife_edge_cells"] <= max(5, 0.15 * melted) and singular.sum() <= 0.05 * N, rep
+    assert rep["knife_edge_cells"] <= max(5, 0.15 * melted) and singular.sum() <= 0.004 * N, rep
     assert not bad, bad
 
 

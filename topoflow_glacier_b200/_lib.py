@@ -70,6 +70,7 @@ PROTOTYPES = {
     "tfg_bind_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
     "tfg_bind_forcing_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "tfg_bind_window_carry": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tfg_bind_mass_residual": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tfg_bind_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "tfg_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                           C.c_int32, C.c_void_p]),

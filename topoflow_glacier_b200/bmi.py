@@ -423,6 +423,9 @@ class BmiTopoflowGlacier(_BmiBase):
             host = np.empty(self._n, dtype=np.float64)
             host[:] = src
             self._engine.row(internal).copy_(torch.as_tensor(host).to(self._engine.dtype))
+            lo = getattr(self._engine, "mass_lo", None)
+            if lo is not None and internal in ("h_swe", "h_iwe"):   # float32 mode: the low part belongs to the old value
+                lo[("h_swe", "h_iwe").index(internal)].zero_()
             self._out_valid = False
 
     def set_value_at_indices(self, name: str, inds: np.ndarray, src: np.ndarray) -> None:

@@ -48,6 +48,7 @@ struct tfg_ctx {
   int64_t exact_agg = 0;  // TFG_OPT_EXACT_AGG value (0 = floating-point atomics)
   const int32_t* forcing_col = nullptr;  // tfg_bind_forcing_map
   void* win_carry = nullptr;             // tfg_bind_window_carry
+  void* mass_lo = nullptr;               // tfg_bind_mass_residual
   int64_t n_cols = 0;
 };
 
@@ -119,6 +120,7 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
   p.forcing = static_cast<const raw*>(forcing);
   p.forcing_col = x->forcing_col;
   p.win_carry = static_cast<raw*>(x->win_carry);
+  p.mass_lo = static_cast<raw*>(x->mass_lo);
   p.n_cols = x->forcing_col ? x->n_cols : x->n_cells;
 #define S(f) p.f = static_cast<const raw*>(x->s.f)
   S(a_elev); S(sin_lat); S(cos_lat); S(neg_tan_lat); S(lon); S(dlon); S(t_noon); S(da_m2);
@@ -340,6 +342,13 @@ int tfg_bind_static(tfg_ctx* x, int64_t n_cells, const tfg_statics* s) {
 int tfg_bind_window_carry(tfg_ctx* x, void* carry) {
   if (!x) return fail("tfg_bind_window_carry: NULL context");
   x->win_carry = carry;
+  return 0;
+}
+
+int tfg_bind_mass_residual(tfg_ctx* x, void* lo) {
+  if (!x) return fail("tfg_bind_mass_residual: NULL context");
+  if (lo && x->mode != TFG_F32) return fail("tfg_bind_mass_residual: only the float32 mode carries low parts");
+  x->mass_lo = lo;
   return 0;
 }
 

@@ -67,7 +67,24 @@ struct TimeRow {  // see tfg_time_row in include/tfglacier.h
 template <class raw>
 struct CellState {
   raw h_snow, h_swe, h_ice, h_iwe, eccs, ecci, albedo, n_days;
+  // float32 mode only: low parts of h_swe / h_iwe.  The water-equivalent balance (:1594-1617) is carried as
+  // (double)h + (double)lo and evaluated in float64 inside the float32 kernel: accumulating hourly melt of 1e-4 m into a
+  // float32 depth of ~1 m loses the melt-out hour, which is where float32 results left the reference
+  raw swe_lo, iwe_lo;
 };
+
+// float32 mode: one water-equivalent balance in float64.  h (+ low part) gains `gain`, then loses min(M*3600, h)/3600*dt*3600;
+// returns the melt rate actually realised.  Same operation order as the reference, so the melt-out residue logic carries over.
+__device__ __forceinline__ float balance64(float& h, float& lo, float gain, float M, float dt) {
+  double w = (double)h + (double)lo;
+  w = w + (double)gain;
+  const double s = fmin((double)M * 3600.0, w);
+  const double m = s / 3600.0;
+  w = fmax(w - (m * (double)dt) * 3600.0, 0.0);
+  h = (float)w;
+  lo = (float)(w - (double)h);
+  return (float)m;
+}
 
 
 // ---- where the per-cell constants and the diagnostic integrals live during a launch ------------------------
@@ -394,10 +411,14 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if constexpr (VOL) s.set(kSVolSM, fmadd((SM * R(s.get(kSDa))) * dt, LIT(c3600, 3600.0), R(s.get(kSVolSM))).v);  // :1486-1487
   // ---- update_swe :1594-1606 (single-rounding ops in every mode: decides whether SWE hits exactly 0)
   const R k3600 = LIT(c3600, 3600.0);
-  h_swe = xadd(h_swe, xmul(P_snow, dt));
-  SM = div3600(nmin(xmul(SM, k3600), h_swe));
-  h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
-  h_swe = relu(h_swe);
+  if constexpr (P::f32) {
+    SM = R(balance64(h_swe.v, st.swe_lo, xmul(P_snow, dt).v, SM.v, dt.v));
+  } else {
+    h_swe = xadd(h_swe, xmul(P_snow, dt));
+    SM = div3600(nmin(xmul(SM, k3600), h_swe));
+    h_swe = xsub(h_swe, xmul(xmul(SM, dt), k3600));
+    h_swe = relu(h_swe);
+  }
   // ---- update_snowfall_cold_content :1507-1537 (T_wb is only consumed where P_snow > 0)
   if (P_snow > 0.0) {
     const R new_h_snow = (P_snow * dt) * R(k.ws_ratio);
@@ -429,9 +450,13 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   if constexpr (P::strict) IM = relu(nmin(IM, zdiv(h_iwe, dt))); else IM = nmin(IM, h_iwe * R(k.inv_dt));
   if constexpr (VOL) s.set(kSVolIM, fmadd((IM * R(s.get(kSDa))) * dt, LIT(c3600, 3600.0), R(s.get(kSVolIM))).v);  // :1493-1494
   // ---- update_iwe :1612-1617 (single-rounding ops, as for SWE)
-  IM = div3600(nmin(xmul(IM, k3600), h_iwe));
-  h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
-  h_iwe = relu(h_iwe);
+  if constexpr (P::f32) {
+    IM = R(balance64(h_iwe.v, st.iwe_lo, 0.0f, IM.v, dt.v));
+  } else {
+    IM = div3600(nmin(xmul(IM, k3600), h_iwe));
+    h_iwe = xsub(h_iwe, xmul(xmul(IM, dt), k3600));
+    h_iwe = relu(h_iwe);
+  }
   // ---- update_combined_meltrate :1441-1445
   R M_total;
   if constexpr (P::strict) M_total = (IM + SM) + divk(P_rain, 3600.0);

@@ -46,6 +46,7 @@ struct RunParams {
   raw *h_snow, *h_swe, *h_ice, *h_iwe, *eccs, *ecci, *albedo, *n_days, *SM, *IM, *M_total, *RH;
   raw *vol_P, *vol_PR, *vol_PS, *vol_SM, *vol_IM, *P_max;
   raw* ring;
+  raw* mass_lo;    // optional [2][n_cells] (float32 mode): low parts of h_swe / h_iwe, see CellState
   raw* win_carry;  // optional [3][n_cells]: incremental window sum, its largest magnitude and its rounding count, carried
                    // from launch to launch so that short launches need not re-read all 72 slots (NaN count = re-seed)
   // Clock-only tables of THIS launch, passed in the kernel parameter block (constant bank): the step index is
@@ -181,6 +182,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   CellState<raw> st;
   st.h_snow = p.h_snow[c]; st.h_swe = p.h_swe[c]; st.h_ice = p.h_ice[c]; st.h_iwe = p.h_iwe[c];
   st.eccs = p.eccs[c]; st.ecci = p.ecci[c]; st.albedo = p.albedo[c]; st.n_days = p.n_days[c];
+  st.swe_lo = st.iwe_lo = 0;
+  if constexpr (P::f32) { if (p.mass_lo != nullptr) { st.swe_lo = p.mass_lo[c]; st.iwe_lo = p.mass_lo[N + c]; } }
   const bool have_vol = VOL && p.vol_P != nullptr;
   s.set(kSVolP, have_vol ? p.vol_P[c] : 0); s.set(kSVolPR, have_vol ? p.vol_PR[c] : 0);
   s.set(kSVolPS, have_vol ? p.vol_PS[c] : 0); s.set(kSVolSM, have_vol ? p.vol_SM[c] : 0);
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     p.h_snow[c] = st.h_snow; p.h_swe[c] = st.h_swe; p.h_ice[c] = st.h_ice; p.h_iwe[c] = st.h_iwe;
     p.eccs[c] = st.eccs; p.ecci[c] = st.ecci; p.albedo[c] = st.albedo; p.n_days[c] = st.n_days;
     p.SM[c] = o.SM; p.IM[c] = o.IM; p.M_total[c] = o.M_total; p.RH[c] = o.RH;
+    if constexpr (P::f32) { if (p.mass_lo != nullptr) { p.mass_lo[c] = st.swe_lo; p.mass_lo[N + c] = st.iwe_lo; } }
     if (have_vol) {
       p.vol_P[c] = s.get(kSVolP); p.vol_PR[c] = s.get(kSVolPR); p.vol_PS[c] = s.get(kSVolPS);
       p.vol_SM[c] = s.get(kSVolSM); p.vol_IM[c] = s.get(kSVolIM); p.P_max[c] = s.get(kSPmax);

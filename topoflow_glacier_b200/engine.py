@@ -171,6 +171,11 @@ class MeltEngine:
         # running sum of the snowfall window carried between launches (tfg_bind_window_carry); NaN count = re-seed
         self.window_carry = torch.full((3, self.N), float("nan"), dtype=self.dtype, device=self.device)
         _lib.check(self.lib.tfg_bind_window_carry(self.ctx, self.window_carry.data_ptr()), "tfg_bind_window_carry")
+        # float32 mode: low parts of h_swe / h_iwe, so that the water-equivalent balances run in float64 (tfg_bind_mass_residual)
+        self.mass_lo = None
+        if self.mode == _lib.F32:
+            self.mass_lo = torch.zeros(2, self.N, dtype=self.dtype, device=self.device)
+            _lib.check(self.lib.tfg_bind_mass_residual(self.ctx, self.mass_lo.data_ptr()), "tfg_bind_mass_residual")
 
     def invalidate_window_sum(self):
         """Call after writing to ``ring`` from outside the kernels: the next launch re-sums the window."""
@@ -329,7 +334,8 @@ class MeltEngine:
         torch.cuda.synchronize(self.device)
         return {"format": 1, "n_cells": self.N, "dtype": str(self.dtype), "mode": self.mode, "step_index": self.step_index,
                 "start": str(self.start), "dt_hours": self.dt_hours, "ring_slots": self.ring_slots,
-                "state": self.state.cpu(), "ring": self.ring.cpu(), "inputs": self.inputs.cpu()}
+                "state": self.state.cpu(), "ring": self.ring.cpu(), "inputs": self.inputs.cpu(),
+                "mass_lo": None if self.mass_lo is None else self.mass_lo.cpu()}
 
     def load_state_dict(self, sd: dict) -> None:
         if sd.get("format") != 1:
@@ -342,6 +348,11 @@ class MeltEngine:
         self.ring.copy_(sd["ring"])
         self.invalidate_window_sum()
         self.inputs.copy_(sd["inputs"])
+        if self.mass_lo is not None:
+            if sd.get("mass_lo") is not None:
+                self.mass_lo.copy_(sd["mass_lo"])
+            else:
+                self.mass_lo.zero_()
         self.step_index = int(sd["step_index"])
         self.ensure_horizon(self.step_index + 1)
 
