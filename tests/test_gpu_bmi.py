@@ -626,7 +626,7 @@ assert torch.equal(m._engine.state, sh.state)
 np.savez({str(tmp_path)!r} + f"/out{{rank}}.npz", agg=torch.cat(parts).cpu().numpy(), state=sh.state.cpu().numpy(),
          lo=lo, hi=hi)
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\\n" % rank)  # one write: two ranks share the pipe
 ''')
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",

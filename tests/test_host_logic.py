@@ -209,7 +209,7 @@ for t in range(T):
         np.testing.assert_allclose(agg.buffer[t, :, j].numpy(), basin_sums_host(vals[t, j], da, basin, NB), rtol=1e-13)
 np.testing.assert_allclose(area.numpy(), np.bincount(basin, weights=da, minlength=NB), rtol=1e-13)
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\\n" % rank)  # one write: two ranks share the pipe
 ''')
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",

@@ -76,13 +76,21 @@ struct CellState {
 // float32 mode: one water-equivalent balance in float64.  h (+ low part) gains `gain`, then loses min(M*3600, h)/3600*dt*3600;
 // returns the melt rate actually realised.  Same operation order as the reference, so the melt-out residue logic carries over.
 __device__ __forceinline__ float balance64(float& h, float& lo, float gain, float M, float dt) {
-  double w = (double)h + (double)lo;
-  w = w + (double)gain;
-  const double s = fmin((double)M * 3600.0, w);
-  const double m = s / 3600.0;
-  w = fmax(w - (m * (double)dt) * 3600.0, 0.0);
+  if (gain == 0.0f && M == 0.0f) return 0.0f;   // nothing enters or leaves (frozen pack, snow-covered ice): h + lo stays as it is
+  // single-rounding intrinsics throughout: this translation unit allows FMA contraction, and a fused w - (m dt) 3600
+  // would return the rounding residue of the product instead of the reference's exact zero at melt-out
+  double w = __dadd_rn((double)h, (double)lo);
+  w = __dadd_rn(w, (double)gain);
+  const double s3 = __dmul_rn((double)M, 3600.0);
+  const double s = (s3 < w) ? s3 : w;                 // both finite and >= 0 here: no NaN handling needed
+  // s / 3600 correctly rounded (Markstein, as div3600 in tfg_num.cuh): the reference's own float64 operations in its
+  // own order, so a pack that melts out leaves a rounding residue exactly when the reference's would
+  const double y = 1.0 / 3600.0, q = __dmul_rn(s, y);
+  const double m = __fma_rn(__fma_rn(-3600.0, q, s), y, q);
+  w = __dsub_rn(w, __dmul_rn(__dmul_rn(m, (double)dt), 3600.0));
+  w = (w > 0.0) ? w : 0.0;
   h = (float)w;
-  lo = (float)(w - (double)h);
+  lo = (float)__dsub_rn(w, (double)h);
   return (float)m;
 }
 
