@@ -94,13 +94,14 @@ tfg::Consts<raw> derive(const tfg_constants& c) {
   k.inv_rstar = 1.0 / c.uni_gas_const;
   k.inv_p0c = 1.0 / (c.sea_level_p0 * 0.01);
   k.kappa2 = c.kappa * c.kappa;
+  k.cq0 = (k.rho_lv_air * k.lhc) * k.inv_p0c;
   k.satterlund = c.satterlund;
   tfg::Consts<raw> r;
 #define CP(f) r.f = static_cast<raw>(k.f)
   CP(dt); CP(days_per_dt); CP(T0); CP(sea_p0); CP(r_star); CP(eps); CP(one_m_eps); CP(gz); CP(z); CP(z0_air);
   CP(kappa); CP(rho_cp_air); CP(rho_lv_air); CP(lhc); CP(ws_ratio); CP(wi_ratio); CP(rho_cp_snow); CP(rho_lf);
   CP(dust); CP(emis_a); CP(emis_b); CP(canopy); CP(sigma); CP(es_sigma); CP(one_m_es); CP(one_seventh); CP(omega);
-  CP(rad2deg); CP(deg2rad); CP(inv_z0); CP(inv_dt); CP(inv_rho_lf); CP(inv_rstar); CP(inv_p0c); CP(kappa2);
+  CP(rad2deg); CP(deg2rad); CP(inv_z0); CP(inv_dt); CP(inv_rho_lf); CP(inv_rstar); CP(inv_p0c); CP(kappa2); CP(cq0);
 #undef CP
   r.satterlund = k.satterlund;
   return r;

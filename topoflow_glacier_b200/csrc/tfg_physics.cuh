@@ -20,6 +20,9 @@ static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.1
 #ifndef TFG_AIRMASS_TABLE   // fast float64: Kasten-Young air mass from the table of tfg_math.cuh (0: closed form, A/B runs)
 #define TFG_AIRMASS_TABLE 1
 #endif
+#ifndef TFG_SPLIT_STEP
+#define TFG_SPLIT_STEP 0
+#endif
 #ifndef TFG_WETBULB_TABLE   // fast float64: Stull wet bulb from the tables of tfg_math.cuh (0: closed form, A/B runs)
 #define TFG_WETBULB_TABLE 1
 #endif
@@ -55,6 +58,7 @@ struct Consts {
   raw deg2rad;       // pi / 180 (solar_funcs.py:566)
   raw inv_z0, inv_dt, inv_rho_lf;  // fast modes only: reciprocals of z0_air, dt, rho_H2O*Lf
   raw inv_rstar, inv_p0c, kappa2;  // fast modes only: 1/R*, 1/(sea_p0*0.01), kappa^2
+  raw cq0;                         // fast float64: rho_air*Lv * latent_heat_constant / (sea_p0*0.01)  (:931-934 folded)
   int satterlund;
 };
 
@@ -239,6 +243,208 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   return fmadd(tau, K_s, K_dif) + K_bs;                      // :909
 }
 
+
+// =====================================================================================================================
+// EXPERIMENT (round 2, not the default path): the fast float64 step in two parts.  Build with -DTFG_SPLIT_STEP=1 (and
+// -DTFG_PIPELINE=1 for the software-pipelined loop of tfg_pipe.cuh).  Measured on the bench shape (16 777 216 cells x
+// 128 steps, profiles/r2_experiments.md): single-stream split step 29.0 G cell-steps/s (inline step: 30.0 G);
+// pipelined loop 22.2 G at 128 registers / 4 blocks per SM, 21.9 G at 96 registers (440 B of spills): the second
+// instruction stream costs more in registers (fewer resident warps, spills) than it returns in overlapped latency --
+// warps issue in order, so it is thread-level parallelism that hides the FP64 latency of this kernel, not ILP.
+//
+// `lean_forcing` is everything of update() that does not read the carried state: the met block up to the dew point
+// (:519-556, :747-893), the vapour factor of the latent heat flux for BOTH surface temperatures the state can select
+// (T_surf = T_dew, or 0 degC over a melting surface, :906-911), incoming longwave (:1167-1234), the clear-sky shortwave
+// except its LINEAR dependence on albedo (K_cs = A + albedo*B, solar_funcs.py:894-953), and the snowfall wet bulb
+// (:1507-1520).  `lean_state` consumes the ten numbers of `Derived` and advances the state (:626-733 log law and bulk
+// exchange, :1006-1059 albedo, :1207-1319 net fluxes, :1321-1617 melt, water equivalents, cold content).
+// The split (a) lets a kernel evaluate the forcing part of step t+1 beside the state part of step t -- two independent
+// instruction streams per thread, where the single-stream step waits out one FP64 latency after the other -- and
+// (b) is the hand-over interface of the producer / consumer kernel (tfg_ws.cuh).  Every instantiation of the fast mode
+// goes through these two functions, so recording / aggregate / integral kernels agree bit for bit.
+// =====================================================================================================================
+template <class raw>
+struct Derived {
+  raw P_signed;  // +P where it rains, -P where it snows (T_air <= T_rain_snow)
+  raw T_air, uz, T_dew;
+  raw Xa, Xb;    // rho_air Lv (0.622/p0) (e_air - RH e_sat(T_surf)) for T_surf = T_dew / T_surf = 0 degC: Qe = De * X
+  raw LW_in;     // em_air sigma T_K^4
+  raw A, B;      // K_cs = A + albedo * B  (both 0 at night)
+  raw ccs;       // rho_snow Cp_snow (P_snow dt rho_H2O/rho_snow) (T0 - T_wb), 0 unless it snows
+  raw RH;        // BMI output
+  // intermediates, read by recording kernels only (dead code otherwise)
+  raw p0, e_sat_air, e_air, es_dew, W_p, em_air, th;
+};
+
+template <class Cell>
+__device__ __forceinline__ void lean_forcing(const Consts<double>& k, const TimeRow<double>& tr, const Cell& s, double LC,
+                                             double Pp, double T_air, double P_air, double q, double uz, Derived<double>& d) {
+  const double T_K = T_air + kLit.kelvin;
+  const bool is_snow = T_air <= s.get(kSTrs);                                   // :585, :604
+  d.P_signed = is_snow ? -Pp : Pp;
+  d.T_air = T_air; d.uz = uz;
+  // -- three reciprocals: 1/T_K, the vapour-pressure quotient (:817), the Magnus quotient of the air (:788)
+  const double den3[3] = {T_K, fma(k.one_m_eps, q, k.eps), T_air + kLit.mag_b};
+  double rc3[3];
+  fm::rcp3_n<3>(den3, rc3);
+  const double rTK = rc3[0];
+  const double e_air = ((q * P_air) * rc3[1]) * kLit.c001;
+  // -- exp(-M g elev / (R* T_K)) (:551-556) and exp(-17.3 T/(T+237.3)); log(e_air/6.1121) (:892)
+  const double ex2[2] = {-((s.get(kSaElev) * k.inv_rstar) * rTK), -((kLit.mag_a * T_air) * rc3[2])};
+  double ey2[2];
+  fm::exp_tab_n<2>(ex2, ey2);
+  const double log_term = fm::log_tab(e_air * kLit.inv_dew_a);
+  const double RH = (e_air * ey2[1]) * kLit.inv_esat0;                          // e_air / (6.11 exp(t1)), :838
+  const double T_dew = (kLit.dew_c * log_term) * fm::rcp3(kLit.dew_b - log_term);   // :888-893
+  // -- W_p = 1.12 exp(0.0614 T_dew) (:919-920) and e_sat(T_dew) (:784-802)
+  const double ex2b[2] = {kLit.wp_b * T_dew, (kLit.mag_a * T_dew) * fm::rcp3(T_dew + kLit.mag_b)};
+  double ey2b[2];
+  fm::exp_tab_n<2>(ex2b, ey2b);
+  const double W_p = kLit.wp_a * ey2b[0];
+  const double es_dew = (kLit.esat0 * ey2b[1]) * 10.0;
+  const double es_zero = (kLit.esat0 * 1.0) * 10.0;                             // e_sat(0 degC), same operations
+  const double cq = ey2[0] * k.cq0;                                             // rho_air Lv * 0.622 / p0, :931-934
+  d.Xa = cq * fma(-RH, es_dew, e_air);
+  d.Xb = cq * fma(-RH, es_zero, e_air);
+  d.T_dew = T_dew; d.RH = RH;
+  // -- update_em_air :1167-1180 (Brutsaert), incoming longwave :1234
+  const double em_air = fma(k.emis_a * fm::root7((e_air * kLit.c01) * rTK), k.emis_b, k.canopy);
+  const double tk2 = T_K * T_K;
+  d.LW_in = (em_air * k.sigma) * (tk2 * tk2);
+  // -- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471 ; Clear_Sky_Radiation solar_funcs.py:894-953
+  const double th = tr.clock_hour - ((kLit.c12 + LC) + tr.TE);
+  const double wt = k.omega * th;
+  const double c_wt = fma(tr.cos_hour, s.get(kSCB), tr.sin_hour * s.get(kSSB));       // cos(omega th) by angle addition
+  const double c_u = fma(tr.cos_hour, s.get(kSCB2), tr.sin_hour * s.get(kSSB2));      // cos(omega th + dlon)
+  const double arg_eq = s.get(kSNegTanEq) * tr.tan_decl, arg_h = s.get(kSNegTanLat) * tr.tan_decl;
+  // th <= -acos(a)/omega or th >= acos(a)/omega  <=>  cos(omega th) <= a  for |omega th| < pi (solar_funcs.py:783-830, :939)
+  const bool dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (fabs(wt) >= kLit.pi) || (fabs(wt + s.get(kSDlon)) >= kLit.pi);
+  d.A = 0.0; d.B = 0.0;
+  if (!dark) {
+    const double cos_lat = s.get(kSCosLat), sin_lat = s.get(kSSinLat);
+    const double cosZ = fma(cos_lat * tr.cos_decl, c_wt, sin_lat * tr.sin_decl);        // :281-284
+    const double t1 = relu(Num<FastF64>(cosZ)).v;
+    const double M_opt = fm::rcp3(fm::inv_air_mass(t1));                                 // :549-568 (Kasten & Young)
+    const double ex[2] = {fma(fma(-kLit.sa_b1, W_p, kLit.sa_b0), M_opt, fma(-kLit.sa_a1, W_p, kLit.sa_a0)),    // :608-614
+                          fma(fma(-kLit.s_b1, W_p, kLit.s_b0), M_opt, fma(-kLit.s_a1, W_p, kLit.s_a0))};      // :649-653
+    double ey[2];
+    fm::exp_tab_n<2>(ex, ey);
+    const double tau = nmin(relu(Num<FastF64>(ey[0] - k.dust)), Num<FastF64>(1.0)).v;
+    const double half_gam = 0.5 * ((1.0 - ey[1]) + k.dust);
+    const double K_h = relu(Num<FastF64>(tr.isc_e0 * fma(tr.cos_decl * cos_lat, c_wt, tr.sin_decl * sin_lat))).v;      // :391-412
+    const double K_s = relu(Num<FastF64>(tr.isc_e0 * fma(tr.cos_decl * s.get(kSCosEq), c_u, s.get(kSSinEq) * tr.sin_decl))).v;  // :866-887
+    const double K_dif = half_gam * K_h;                                                 // :667
+    d.A = fma(tau, K_s, K_dif);                                                          // :909 without backscatter
+    d.B = half_gam * fma(tau, K_h, K_dif);                                               // :711: K_bs = albedo * B
+  }
+  // -- update_snowfall_cold_content :1507-1537: the wet bulb is only consumed where snow falls
+  d.ccs = 0.0;
+  if (is_snow && Pp > 0.0) {
+    double T_wb;
+    if (RH >= 0.046875 && RH <= 2.0) {          // table bins 1..32
+      T_wb = fm::stull_wet_bulb_tab(T_air, RH);
+    } else {
+      using R = Num<FastF64>;
+      const R T(T_air), H(RH);
+      T_wb = (((((T * natan(R(kLit.st_a) * nsqrt(H + R(kLit.st_b)))) + natan(T + H)) - natan(H - R(kLit.st_c))) +
+               ((R(kLit.st_d) * npow15(H)) * natan(R(kLit.st_e) * H))) - R(kLit.st_f)).v;
+    }
+    d.ccs = (k.rho_cp_snow * ((Pp * k.dt) * k.ws_ratio)) * (k.T0 - T_wb);
+  }
+  d.p0 = fm::div_fast(1.0, ey2[0] * k.inv_p0c); d.e_sat_air = fm::div_fast(kLit.esat10, ey2[1]); d.e_air = e_air;
+  d.es_dew = es_dew; d.W_p = W_p; d.em_air = em_air; d.th = th;
+}
+
+template <bool VOL, class Cell, class WindowFn>
+__device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, CellState<double>& st, const Derived<double>& d,
+                                           WindowFn&& window_sum, StepOut<double>& o) {
+  using R = Num<FastF64>;
+  const double dt = k.dt;
+  double h_snow = st.h_snow, h_swe = st.h_swe, h_ice = st.h_ice, h_iwe = st.h_iwe, Eccs = st.eccs, Ecci = st.ecci;
+  const double P_rain = relu(R(d.P_signed)).v, P_snow = relu(R(-d.P_signed)).v;
+  const double Pp = fabs(d.P_signed), T_air = d.T_air, uz = d.uz, T_dew = d.T_dew;
+  if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
+    const double da = s.get(kSDa);
+    s.set(kSVolP, fma(Pp * da, dt, s.get(kSVolP)));
+    s.set(kSPmax, nmax(R(s.get(kSPmax)), R(Pp)).v);
+    s.set(kSVolPR, fma(P_rain * da, dt, s.get(kSVolPR)));
+    s.set(kSVolPS, fma(P_snow * da, dt, s.get(kSVolPS)));
+  }
+  const double T_K = T_air + kLit.kelvin;
+  // -- update_T_surf :906-911: min(T_dew, 0) over snow or ice; e_sat(T_surf) is then e_sat(0) or e_sat(T_dew)
+  const bool warm = ((h_snow > 0.0) || (h_ice > 0.0)) && (T_dew > 0.0);
+  const double T_surf = warm ? 0.0 : T_dew;
+  const double X = warm ? d.Xb : d.Xa;
+  // -- update_bulk_richardson_number :640-644, update_bulk_aero_conductance :670-733 as ONE quotient:
+  //    stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
+  //    unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
+  const double dT = T_air - T_surf;
+  const double top = k.gz * dT;
+  double bot = (uz * uz) * T_K;
+  bot = (bot == 0.0) ? kLit.c001 : bot;
+  const bool stable = top > 0.0;
+  const double num = stable ? bot : fma(-10.0, top, bot);
+  const double den = stable ? fma(10.0, top, bot) : bot;
+  const double L = fm::log_tab(nmax(R((k.z - h_snow) * k.inv_z0), R(kLit.c001)).v);
+  const double uk2 = uz * k.kappa2, LL = L * L;
+  const double Dh = (uk2 * num) * fm::rcp3(LL * den);
+  const double Qh = (k.rho_cp_air * Dh) * dT;                                   // :744-745
+  const double Qe = Dh * X;                                                     // :931-934
+  // -- update_albedo("aging") :1023-1059
+  const double r = (T_air > 0.0) ? kLit.alb_r1 : kLit.alb_r0;
+  const double ring_new = __dmul_rn(__dmul_rn(P_snow, dt), k.ws_ratio);         // :1031-1033
+  const double tot = window_sum(ring_new);                                      // :1027-1037
+  double n = st.n_days;
+  n = (tot < kLit.snow_thr) ? n + k.days_per_dt : 0.0;                          // :1040-1041 (tot is finite on the sane path)
+  double albedo = st.albedo;
+  if (h_snow > 0.0) albedo = fma(kLit.alb_k, fm::exp_tab((-n) * r), kLit.alb_0);        // :1042-1048
+  if (h_snow == 0.0 && h_ice > 0.0) albedo = kLit.alb_ice;                      // :1049-1053
+  if (h_snow == 0.0 && h_ice == 0.0) albedo = kLit.alb_bare;                    // :1054-1058
+  // -- net shortwave :1122-1139 (K_cs = A + albedo B), net longwave :1231-1248, energy sum :1314
+  const double Qn_SW = fma(albedo, d.B, d.A) * (1.0 - albedo);
+  const double T_surf_K = T_surf + kLit.kelvin, ts2 = T_surf_K * T_surf_K;
+  const double LW_out = fma(k.one_m_es, d.LW_in, k.es_sigma * (ts2 * ts2));
+  const double Qn_LW = d.LW_in - LW_out;
+  const double Q_sum = ((Qn_SW + Qn_LW) + Qh) + Qe;
+  // -- snow: update_snow_meltrate :1364-1368, enforce_max_snow_meltrate :1465
+  const double previous_swe = h_swe;                                            // :1571
+  const double E_in = Q_sum * dt;
+  double SM = (relu(R(E_in - Eccs)).v * k.inv_dt) * k.inv_rho_lf;
+  if constexpr (VOL) s.set(kSVolSM, fma((SM * s.get(kSDa)) * dt, kLit.c3600, s.get(kSVolSM)));   // :1486-1487
+  // -- update_swe :1594-1606 (single-rounding operations: decides whether SWE reaches exactly 0)
+  h_swe = __dadd_rn(h_swe, __dmul_rn(P_snow, dt));
+  SM = div3600(nmin(R(__dmul_rn(SM, kLit.c3600)), R(h_swe))).v;
+  h_swe = relu(R(__dsub_rn(h_swe, __dmul_rn(__dmul_rn(SM, dt), kLit.c3600)))).v;
+  // -- update_snowfall_cold_content :1533-1537
+  if (P_snow > 0.0) Eccs = relu(R((Eccs + d.ccs) - E_in)).v;
+  // -- update_ice_meltrate :1418-1428 (NEW h_swe, OLD h_ice), enforce_max_ice_meltrate :1473-1480
+  double IM = (relu(R(E_in - Ecci)).v * k.inv_dt) * k.inv_rho_lf;
+  IM = ((h_swe == 0.0) && (previous_swe == 0.0)) ? IM : 0.0;
+  Ecci = relu(R(Ecci - E_in)).v;
+  Ecci = (h_ice == 0.0) ? 0.0 : Ecci;
+  IM = nmin(R(IM), R(h_iwe * k.inv_dt)).v;
+  if constexpr (VOL) s.set(kSVolIM, fma((IM * s.get(kSDa)) * dt, kLit.c3600, s.get(kSVolIM)));   // :1493-1494
+  // -- update_iwe :1612-1617
+  IM = div3600(nmin(R(__dmul_rn(IM, kLit.c3600)), R(h_iwe))).v;
+  h_iwe = relu(R(__dsub_rn(h_iwe, __dmul_rn(__dmul_rn(IM, dt), kLit.c3600)))).v;
+  const double M_total = fma(P_rain, 1.0 / 3600.0, IM + SM);                    // :1441-1445
+  h_snow = __dmul_rn(h_swe, k.ws_ratio);                                        // :1711
+  h_ice = __dmul_rn(h_iwe, k.wi_ratio);                                         // :1726
+  // -- update_snowpack_cold_content :1552-1558
+  if (P_snow <= 0.0) Eccs = relu(R(Eccs - E_in)).v;
+  if (h_snow == 0.0) Eccs = 0.0;
+
+  st.h_snow = h_snow; st.h_swe = h_swe; st.h_ice = h_ice; st.h_iwe = h_iwe;
+  st.eccs = Eccs; st.ecci = Ecci; st.albedo = albedo; st.n_days = n;
+  o.SM = SM; o.IM = IM; o.M_total = M_total; o.RH = d.RH;
+  // intermediates: only read when a caller records them (dead code otherwise)
+  const double e_sat_surf = warm ? (kLit.esat0 * 1.0) * 10.0 : d.es_dew;
+  o.p0 = d.p0; o.e_sat_air = d.e_sat_air; o.e_air = d.e_air; o.T_dew = T_dew; o.T_surf = T_surf; o.e_sat_surf = e_sat_surf;
+  o.Ri = fm::div_fast(top, bot); o.Dn = fm::div_fast(uk2, LL); o.Dh = Dh; o.Qh = Qh; o.W_p = d.W_p;
+  o.e_surf = d.RH * e_sat_surf; o.Qe = Qe; o.th = d.th; o.Qn_SW = Qn_SW; o.em_air = d.em_air; o.Qn_LW = Qn_LW;
+  o.Q_sum = Q_sum; o.P_rain = P_rain; o.P_snow = P_snow;
+}
+
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
 // `mid_step()` is called once the pressure / humidity / wind forcings are dead (after the turbulent fluxes): the
@@ -249,6 +455,15 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
                                           Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
                                           WindowFn&& window_sum, MidFn&& mid_step, StepOut<typename P::raw>& o) {
   using R = Num<P>;
+#if TFG_SPLIT_STEP   // experiment: the fast float64 step through lean_forcing / lean_state (measured 3 % slower, see below)
+  if constexpr (P::lean) {
+    Derived<double> d;
+    lean_forcing(k, tr, s, LC.v, Pp.v, T_air.v, P_air.v, q.v, uz.v, d);
+    mid_step();
+    lean_state<VOL>(k, s, st, d, window_sum, o);
+    return;
+  }
+#endif
   const R dt(k.dt);
   R h_snow(st.h_snow), h_swe(st.h_swe), h_ice(st.h_ice), h_iwe(st.h_iwe), Eccs(st.eccs), Ecci(st.ecci);
 
