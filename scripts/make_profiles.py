@@ -6,6 +6,9 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT, SRC = ROOT / "profiles", ROOT / "gpurun_out"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OUT.mkdir(exist_ok=True)
+# workload of the ncu --set full captures: round 1 used the small fixed workload, round 2 the BENCH shape
+CELLS, STEPS = (2097152, 24) if tag == "r1" else (16777216, 128)
+WORK = f"scripts/prof_run.py: {CELLS:,} cells x {STEPS} steps".replace(",", " ")
 
 
 def launches(csv_path: Path, dst: Path):
@@ -51,9 +54,9 @@ if tcsv.exists():
         "f64_fast:16777216x128": tot, "_source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, {tcsv.name}, one launch "
         "of tfg::run_kernel<FastF64,0,1,1> at the bench configuration", "_kernel_ns_under_ncu": dur}, indent=1) + "\n")
 for rep in sorted(SRC.glob(f"prof_{tag}_*.ncu-rep")):
-    cs = sys.argv[2] if len(sys.argv) > 2 else str(2097152 * 24)
+    cs = sys.argv[2] if len(sys.argv) > 2 else str(CELLS * STEPS)
     txt = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_summary.py"), str(rep), cs], capture_output=True, text=True).stdout
-    (OUT / f"{tag}_{rep.stem}.txt").write_text(f"# ncu --set full, {rep.name}; workload scripts/prof_run.py: 2 097 152 cells x 24 steps\n" + txt)
+    (OUT / f"{tag}_{rep.stem}.txt").write_text(f"# ncu --set full, {rep.name}; workload {WORK}\n" + txt)
 # instruction mix of the hot kernel -> profiles/kernel_mix.json (bench.py turns it into the FP64-pipe ceiling)
 mix = {}
 for mode in ("f64_fast", "f64", "f32"):
@@ -74,11 +77,20 @@ for mode in ("f64_fast", "f64", "f32"):
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))
     m = dict(zip(rr[0], rr[2]))
-    warp_steps = 2097152 * 24 / 32
+    warp_steps = CELLS * STEPS / 32
+    if mode == "f64_fast" and tag != "r1":   # DRAM traffic of the benched instantiation at the bench shape, same capture
+        def num(key):
+            v, u = m.get(key, "0"), dict(zip(rr[0], rr[1])).get(key, "byte")
+            return float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
+        (OUT / "traffic.json").write_text(json.dumps({
+            f"f64_fast:{CELLS}x{STEPS}": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+            "_source": f"ncu --set full ({rep.name}): dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of "
+                       "tfg::run_kernel<FastF64,0,1,1,0> at the bench shape", "_kernel": m.get("Kernel Name", "")}, indent=1) + "\n")
     mix[mode] = {"warp_inst_per_warp_step": tot / warp_steps, "fp64_warp_inst_per_warp_step": fp64 / warp_steps,
                  "fp64_pipe_active_pct": float(m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 0)),
                  "issue_active_pct": float(m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0)),
-                 "source": f"ncu --set full, {rep.name}, scripts/prof_run.py (2 097 152 cells x 24 steps)"}
+                 "kernel": m.get("Kernel Name", ""),
+                 "source": f"ncu --set full, {rep.name}, {WORK}"}
 if mix:
     (OUT / "kernel_mix.json").write_text(json.dumps(mix, indent=1) + "\n")
 for b in sorted(SRC.glob(f"bench_{tag}_*.json")) + sorted(SRC.glob("bench_*gpu*.json")):

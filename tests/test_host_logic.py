@@ -142,6 +142,33 @@ def test_shipped_forcing_samples_and_configs():
     assert isinstance(yaml.safe_load(open(ROOT / "config" / "cat-3062784.yaml"))["start_time"], int)
 
 
+def test_netcdf_forcing_reader_packed_and_float(tmp_path):
+    """NetCDF forcing files behind the same [T, 6, N] block contract as the CSV reader: the file's own int16 packing is
+    handed on unchanged (scale_factor / add_offset), a float file or packed=False gives float64 columns; the time window
+    is applied; the unpacked values equal the CSV's within the resolution of the packing."""
+    import pandas as pd
+
+    from topoflow_glacier_b200.forcing import (DEFAULT_PACKING, RAW_COLUMNS, read_forcing_csv, read_forcing_netcdf,
+                                                 unpack_forcing, write_forcing_netcdf)
+
+    csv = ROOT / "tests" / "data" / "sample-cat-3062920.csv"
+    raw = read_forcing_csv(csv)                                          # [288, 6]
+    when = pd.to_datetime(pd.read_csv(csv)["Time"])
+    block = np.repeat(raw[:, :, None], 3, axis=2) * np.array([1.0, 1.001, 0.999])[None, None, :]
+    nc = tmp_path / "forcing.nc"
+    write_forcing_netcdf(nc, pd.DatetimeIndex(when), block)
+    packed, packing = read_forcing_netcdf(nc)
+    assert packed.dtype == np.int16 and packed.shape == (288, 6, 3)
+    assert np.array_equal(packing[0], DEFAULT_PACKING[0]) and np.array_equal(packing[1], DEFAULT_PACKING[1])
+    err = np.abs(unpack_forcing(packed, packing) - block).max(axis=(0, 2))
+    assert (err <= DEFAULT_PACKING[0] / 2 + 1e-9).all(), err
+    flt, none = read_forcing_netcdf(nc, packed=False)
+    assert none is None and flt.dtype == np.float64 and np.array_equal(flt, unpack_forcing(packed, packing))
+    win, _ = read_forcing_netcdf(nc, pd.Timestamp("2013-03-21 00:00"), pd.Timestamp("2013-03-21 23:00"))
+    assert win.shape == (24, 6, 3) and np.array_equal(win, packed[24:48])
+    assert RAW_COLUMNS == ("RAINRATE", "T2D", "PSFC", "Q2D", "U2D", "V2D")
+
+
 def test_shard_bounds_cover_all_cells():
     from topoflow_glacier_b200.sharding import shard_bounds, shard_sizes
 

@@ -23,7 +23,8 @@ import numpy as np
 import pandas as pd
 
 __all__ = ["RAW_COLUMNS", "read_forcing_csv", "stack_catchments", "convert_on_host", "ForcingStreamer",
-           "DEFAULT_PACKING", "pack_forcing", "unpack_forcing", "bind_host_to_gpu"]
+           "DEFAULT_PACKING", "pack_forcing", "unpack_forcing", "bind_host_to_gpu", "read_forcing_netcdf",
+           "write_forcing_netcdf"]
 
 # raw met columns moved to the device, in kernel order (tfg_convert_forcing)
 RAW_COLUMNS = ("RAINRATE", "T2D", "PSFC", "Q2D", "U2D", "V2D")
@@ -81,6 +82,74 @@ def unpack_forcing(packed: np.ndarray, packing=DEFAULT_PACKING) -> np.ndarray:
     """Host statement of what the device computes from packed columns: ``int16 * scale + offset`` in float64."""
     scale, offset = (np.asarray(a, dtype=np.float64).reshape(1, 6, 1) for a in packing)
     return packed.astype(np.float64) * scale + offset
+
+
+def read_forcing_netcdf(path, start: Optional[pd.Timestamp] = None, end: Optional[pd.Timestamp] = None, packed: bool = True):
+    """One NetCDF (classic / 64-bit offset) forcing file -> the block contract of ``ForcingStreamer``.
+
+    Layout expected (what NWM / AORC style per-catchment archives hold): a ``time`` variable (seconds since the epoch, or
+    with a CF ``units = "<seconds|minutes|hours> since YYYY-MM-DD HH:MM:SS"`` attribute) and the six ``RAW_COLUMNS`` as
+    variables ``[time, cell]`` (or ``[time]`` for one catchment), stored either as floats or as int16 with the CF
+    attributes ``scale_factor`` / ``add_offset``.
+
+    ``packed=True`` and all six variables int16: returns ``(int16 [T, 6, N], (scale[6], offset[6]))`` -- the file's own
+    packing goes to the device unchanged (12 B per cell-step over PCIe, ``ForcingStreamer(raw_dtype="int16",
+    packing=...)``).  Otherwise returns ``(float64 [T, 6, N], None)`` with the packing applied on the host.
+    Read with ``scipy.io.netcdf_file`` (NetCDF-4 / HDF5 files need a converter; no HDF5 library is assumed)."""
+    from scipy.io import netcdf_file
+
+    with netcdf_file(str(path), "r", mmap=False) as nc:
+        missing = [c for c in ("time",) + RAW_COLUMNS if c not in nc.variables]
+        if missing:
+            raise KeyError(f"{path}: missing forcing variables {missing}")
+        tv = nc.variables["time"]
+        units = getattr(tv, "units", b"seconds since 1970-01-01 00:00:00")
+        units = units.decode() if isinstance(units, bytes) else str(units)
+        step, _, origin = units.partition(" since ")
+        when = pd.Timestamp(origin.strip() or "1970-01-01") + pd.to_timedelta(np.asarray(tv[:], dtype=np.float64),
+                                                                            unit={"seconds": "s", "minutes": "min", "hours": "h"}
+                                                                            .get(step.strip().lower(), "s"))
+        keep = np.ones(len(when), dtype=bool)
+        if start is not None:
+            keep &= np.asarray(when >= start)
+        if end is not None:
+            keep &= np.asarray(when <= end)
+        cols, scale, offset, all_i16 = [], [], [], True
+        for name in RAW_COLUMNS:
+            v = nc.variables[name]
+            a = np.array(v[:])
+            a = a.reshape(a.shape[0], -1)[keep]
+            if a.dtype.kind == "i" and a.dtype.itemsize == 2:
+                a = a.astype(np.int16)          # NetCDF stores big-endian; the device wants native int16
+            scale.append(float(getattr(v, "scale_factor", 1.0)))
+            offset.append(float(getattr(v, "add_offset", 0.0)))
+            cols.append(a)
+            all_i16 &= a.dtype == np.int16
+    if packed and all_i16:
+        return np.ascontiguousarray(np.stack(cols, axis=1)), (np.array(scale), np.array(offset))
+    out = np.stack([c.astype(np.float64) * s + o if (s != 1.0 or o != 0.0) else c.astype(np.float64)
+                    for c, s, o in zip(cols, scale, offset)], axis=1)
+    return np.ascontiguousarray(out), None
+
+
+def write_forcing_netcdf(path, when: pd.DatetimeIndex, raw: np.ndarray, packing=DEFAULT_PACKING) -> None:
+    """Write ``raw`` ([T, 6, N] float) as a packed NetCDF-3 forcing file (int16 + scale_factor / add_offset) -- the
+    counterpart of ``read_forcing_netcdf``, used by the tests and by drivers that convert CSV archives once."""
+    from scipy.io import netcdf_file
+
+    packed = pack_forcing(raw, packing)
+    T, _, N = packed.shape
+    with netcdf_file(str(path), "w", version=2) as nc:
+        nc.createDimension("time", T)
+        nc.createDimension("cell", N)
+        tv = nc.createVariable("time", "f8", ("time",))
+        tv.units = "seconds since 1970-01-01 00:00:00"
+        tv[:] = (pd.DatetimeIndex(when) - pd.Timestamp("1970-01-01")) / pd.Timedelta(seconds=1)
+        for j, name in enumerate(RAW_COLUMNS):
+            v = nc.createVariable(name, "i2", ("time", "cell"))
+            v.scale_factor = np.float64(packing[0][j])    # (a Python float would be stored as float32)
+            v.add_offset = np.float64(packing[1][j])
+            v[:] = packed[:, j, :]
 
 
 def bind_host_to_gpu(device_index: int) -> bool:
