@@ -93,7 +93,7 @@ for mode in ("f64_fast", "f64", "f32"):
                  "source": f"ncu --set full, {rep.name}, {WORK}"}
 if mix:
     (OUT / "kernel_mix.json").write_text(json.dumps(mix, indent=1) + "\n")
-for b in sorted(SRC.glob(f"bench_{tag}_*.json")) + sorted(SRC.glob("bench_*gpu*.json")):
+for b in sorted(SRC.glob(f"bench_{tag}_*.json")):   # only this round's lines (gpurun_out/ keeps older rounds' files)
     try:
         line = json.loads(b.read_text().strip().splitlines()[-1])
         (OUT / f"{tag}_{b.stem}.json").write_text(json.dumps(line, indent=1) + "\n")
