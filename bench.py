@@ -617,8 +617,9 @@ def run_gpu_arm(args):
         streamer2 = ForcingStreamer(eng, Ts, raw_dtype="float32")
         agg_s = [BasinAggregates(Ts, N_BASIN, device=dev, exponents=agg_exps) for _ in range(2)]
         agg_sh = [torch.empty(Ts, N_BASIN, 3, dtype=torch.float64).pin_memory() for _ in range(2)]
-        t_sh = timed_e2e(lambda k: e2e_loop(streamer2, raw_cols, agg_s, agg_sh, k), args.e2e_steps)
-        shared = {"value": total_cells * Ts * args.e2e_steps / t_sh, "unit": UNIT,
+        n_sh = 2 * args.e2e_steps   # the last block's D2H is not overlapped: amortise it over a few more blocks
+        t_sh = timed_e2e(lambda k: e2e_loop(streamer2, raw_cols, agg_s, agg_sh, k), n_sh)
+        shared = {"value": total_cells * Ts * n_sh / t_sh, "unit": UNIT, "steps": n_sh,
                   "h2d_bytes_per_step": raw_cols.numel() * raw_cols.element_size(),
                   "d2h_bytes_per_step": out_host[0].numel() * out_host[0].element_size() + agg_sh[0].numel() * 8,
                   "timesteps_per_step": Ts, "forcing_columns": N_BASIN, "out_dtype": args.e2e_out,
