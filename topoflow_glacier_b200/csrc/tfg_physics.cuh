@@ -263,17 +263,26 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
 // (b) is the hand-over interface of the producer / consumer kernel (tfg_ws.cuh).  Every instantiation of the fast mode
 // goes through these two functions, so recording / aggregate / integral kernels agree bit for bit.
 // =====================================================================================================================
+enum { kD_P, kD_Tair, kD_uz, kD_Tdew, kD_Xa, kD_Xb, kD_LWin, kD_A, kD_B, kD_ccs, kDHand,   // the ten hand-over values
+       kD_RH = kDHand, kD_p0, kD_esat_air, kD_eair, kD_esdew, kD_Wp, kD_emair, kD_th, kDCount };  // + output / recording only
+//   kD_P     +P where it rains, -P where it snows (T_air <= T_rain_snow)
+//   kD_Xa/Xb rho_air Lv (0.622/p0) (e_air - RH e_sat(T_surf)) for T_surf = T_dew / T_surf = 0 degC: Qe = De * X
+//   kD_LWin  em_air sigma T_K^4          kD_A/B  K_cs = A + albedo * B (both 0 at night)
+//   kD_ccs   rho_snow Cp_snow (P_snow dt rho_H2O/rho_snow) (T0 - T_wb), 0 unless it snows
 template <class raw>
-struct Derived {
-  raw P_signed;  // +P where it rains, -P where it snows (T_air <= T_rain_snow)
-  raw T_air, uz, T_dew;
-  raw Xa, Xb;    // rho_air Lv (0.622/p0) (e_air - RH e_sat(T_surf)) for T_surf = T_dew / T_surf = 0 degC: Qe = De * X
-  raw LW_in;     // em_air sigma T_K^4
-  raw A, B;      // K_cs = A + albedo * B  (both 0 at night)
-  raw ccs;       // rho_snow Cp_snow (P_snow dt rho_H2O/rho_snow) (T0 - T_wb), 0 unless it snows
-  raw RH;        // BMI output
-  // intermediates, read by recording kernels only (dead code otherwise)
-  raw p0, e_sat_air, e_air, es_dew, W_p, em_air, th;
+struct Derived {            // in registers (single-stream kernels)
+  raw v[kDCount];
+  __device__ __forceinline__ raw get(int i) const { return v[i]; }
+};
+struct SmemDerived {        // one stage of the producer -> consumer ring in shared memory (tfg_ws.cuh): value i of this
+  unsigned base;            // thread's cell at base + i * stride bytes, read at the point of use
+  unsigned stride;
+  __device__ __forceinline__ double get(int i) const {
+    if (i >= kDHand) return 0.0;   // output / recording values do not travel (the producer stores RH itself)
+    double x;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(x) : "r"(base + (unsigned)i * stride));
+    return x;
+  }
 };
 
 template <class Cell>
@@ -281,8 +290,8 @@ __device__ __forceinline__ void lean_forcing(const Consts<double>& k, const Time
                                              double Pp, double T_air, double P_air, double q, double uz, Derived<double>& d) {
   const double T_K = T_air + kLit.kelvin;
   const bool is_snow = T_air <= s.get(kSTrs);                                   // :585, :604
-  d.P_signed = is_snow ? -Pp : Pp;
-  d.T_air = T_air; d.uz = uz;
+  d.v[kD_P] = is_snow ? -Pp : Pp;
+  d.v[kD_Tair] = T_air; d.v[kD_uz] = uz;
   // -- three reciprocals: 1/T_K, the vapour-pressure quotient (:817), the Magnus quotient of the air (:788)
   const double den3[3] = {T_K, fma(k.one_m_eps, q, k.eps), T_air + kLit.mag_b};
   double rc3[3];
@@ -304,13 +313,13 @@ __device__ __forceinline__ void lean_forcing(const Consts<double>& k, const Time
   const double es_dew = (kLit.esat0 * ey2b[1]) * 10.0;
   const double es_zero = (kLit.esat0 * 1.0) * 10.0;                             // e_sat(0 degC), same operations
   const double cq = ey2[0] * k.cq0;                                             // rho_air Lv * 0.622 / p0, :931-934
-  d.Xa = cq * fma(-RH, es_dew, e_air);
-  d.Xb = cq * fma(-RH, es_zero, e_air);
-  d.T_dew = T_dew; d.RH = RH;
+  d.v[kD_Xa] = cq * fma(-RH, es_dew, e_air);
+  d.v[kD_Xb] = cq * fma(-RH, es_zero, e_air);
+  d.v[kD_Tdew] = T_dew; d.v[kD_RH] = RH;
   // -- update_em_air :1167-1180 (Brutsaert), incoming longwave :1234
   const double em_air = fma(k.emis_a * fm::root7((e_air * kLit.c01) * rTK), k.emis_b, k.canopy);
   const double tk2 = T_K * T_K;
-  d.LW_in = (em_air * k.sigma) * (tk2 * tk2);
+  d.v[kD_LWin] = (em_air * k.sigma) * (tk2 * tk2);
   // -- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471 ; Clear_Sky_Radiation solar_funcs.py:894-953
   const double th = tr.clock_hour - ((kLit.c12 + LC) + tr.TE);
   const double wt = k.omega * th;
@@ -319,7 +328,7 @@ __device__ __forceinline__ void lean_forcing(const Consts<double>& k, const Time
   const double arg_eq = s.get(kSNegTanEq) * tr.tan_decl, arg_h = s.get(kSNegTanLat) * tr.tan_decl;
   // th <= -acos(a)/omega or th >= acos(a)/omega  <=>  cos(omega th) <= a  for |omega th| < pi (solar_funcs.py:783-830, :939)
   const bool dark = (c_wt <= arg_h) || (c_u <= arg_eq) || (fabs(wt) >= kLit.pi) || (fabs(wt + s.get(kSDlon)) >= kLit.pi);
-  d.A = 0.0; d.B = 0.0;
+  d.v[kD_A] = 0.0; d.v[kD_B] = 0.0;
   if (!dark) {
     const double cos_lat = s.get(kSCosLat), sin_lat = s.get(kSSinLat);
     const double cosZ = fma(cos_lat * tr.cos_decl, c_wt, sin_lat * tr.sin_decl);        // :281-284
@@ -334,11 +343,11 @@ __device__ __forceinline__ void lean_forcing(const Consts<double>& k, const Time
     const double K_h = relu(Num<FastF64>(tr.isc_e0 * fma(tr.cos_decl * cos_lat, c_wt, tr.sin_decl * sin_lat))).v;      // :391-412
     const double K_s = relu(Num<FastF64>(tr.isc_e0 * fma(tr.cos_decl * s.get(kSCosEq), c_u, s.get(kSSinEq) * tr.sin_decl))).v;  // :866-887
     const double K_dif = half_gam * K_h;                                                 // :667
-    d.A = fma(tau, K_s, K_dif);                                                          // :909 without backscatter
-    d.B = half_gam * fma(tau, K_h, K_dif);                                               // :711: K_bs = albedo * B
+    d.v[kD_A] = fma(tau, K_s, K_dif);                                                          // :909 without backscatter
+    d.v[kD_B] = half_gam * fma(tau, K_h, K_dif);                                               // :711: K_bs = albedo * B
   }
   // -- update_snowfall_cold_content :1507-1537: the wet bulb is only consumed where snow falls
-  d.ccs = 0.0;
+  d.v[kD_ccs] = 0.0;
   if (is_snow && Pp > 0.0) {
     double T_wb;
     if (RH >= 0.046875 && RH <= 2.0) {          // table bins 1..32
@@ -349,20 +358,21 @@ __device__ __forceinline__ void lean_forcing(const Consts<double>& k, const Time
       T_wb = (((((T * natan(R(kLit.st_a) * nsqrt(H + R(kLit.st_b)))) + natan(T + H)) - natan(H - R(kLit.st_c))) +
                ((R(kLit.st_d) * npow15(H)) * natan(R(kLit.st_e) * H))) - R(kLit.st_f)).v;
     }
-    d.ccs = (k.rho_cp_snow * ((Pp * k.dt) * k.ws_ratio)) * (k.T0 - T_wb);
+    d.v[kD_ccs] = (k.rho_cp_snow * ((Pp * k.dt) * k.ws_ratio)) * (k.T0 - T_wb);
   }
-  d.p0 = fm::div_fast(1.0, ey2[0] * k.inv_p0c); d.e_sat_air = fm::div_fast(kLit.esat10, ey2[1]); d.e_air = e_air;
-  d.es_dew = es_dew; d.W_p = W_p; d.em_air = em_air; d.th = th;
+  d.v[kD_p0] = fm::div_fast(1.0, ey2[0] * k.inv_p0c); d.v[kD_esat_air] = fm::div_fast(kLit.esat10, ey2[1]); d.v[kD_eair] = e_air;
+  d.v[kD_esdew] = es_dew; d.v[kD_Wp] = W_p; d.v[kD_emair] = em_air; d.v[kD_th] = th;
 }
 
-template <bool VOL, class Cell, class WindowFn>
-__device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, CellState<double>& st, const Derived<double>& d,
+template <bool VOL, class Cell, class D, class WindowFn>
+__device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, CellState<double>& st, const D& d,
                                            WindowFn&& window_sum, StepOut<double>& o) {
   using R = Num<FastF64>;
   const double dt = k.dt;
   double h_snow = st.h_snow, h_swe = st.h_swe, h_ice = st.h_ice, h_iwe = st.h_iwe, Eccs = st.eccs, Ecci = st.ecci;
-  const double P_rain = relu(R(d.P_signed)).v, P_snow = relu(R(-d.P_signed)).v;
-  const double Pp = fabs(d.P_signed), T_air = d.T_air, uz = d.uz, T_dew = d.T_dew;
+  const double P_signed = d.get(kD_P);
+  const double P_rain = relu(R(P_signed)).v, P_snow = relu(R(-P_signed)).v;
+  const double Pp = fabs(P_signed), T_air = d.get(kD_Tair), uz = d.get(kD_uz), T_dew = d.get(kD_Tdew);
   if constexpr (VOL) {  // :567-568, :576, :613-614, :623-624
     const double da = s.get(kSDa);
     s.set(kSVolP, fma(Pp * da, dt, s.get(kSVolP)));
@@ -374,7 +384,7 @@ __device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, Cel
   // -- update_T_surf :906-911: min(T_dew, 0) over snow or ice; e_sat(T_surf) is then e_sat(0) or e_sat(T_dew)
   const bool warm = ((h_snow > 0.0) || (h_ice > 0.0)) && (T_dew > 0.0);
   const double T_surf = warm ? 0.0 : T_dew;
-  const double X = warm ? d.Xb : d.Xa;
+  const double X = warm ? d.get(kD_Xb) : d.get(kD_Xa);
   // -- update_bulk_richardson_number :640-644, update_bulk_aero_conductance :670-733 as ONE quotient:
   //    stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
   //    unstable (top <= 0): Dh = Dn * (1 - 10 top/bot) = uz k^2 (bot - 10 top) / (L^2 bot)       (top = 0: Dh = Dn)
@@ -401,10 +411,11 @@ __device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, Cel
   if (h_snow == 0.0 && h_ice > 0.0) albedo = kLit.alb_ice;                      // :1049-1053
   if (h_snow == 0.0 && h_ice == 0.0) albedo = kLit.alb_bare;                    // :1054-1058
   // -- net shortwave :1122-1139 (K_cs = A + albedo B), net longwave :1231-1248, energy sum :1314
-  const double Qn_SW = fma(albedo, d.B, d.A) * (1.0 - albedo);
+  const double Qn_SW = fma(albedo, d.get(kD_B), d.get(kD_A)) * (1.0 - albedo);
   const double T_surf_K = T_surf + kLit.kelvin, ts2 = T_surf_K * T_surf_K;
-  const double LW_out = fma(k.one_m_es, d.LW_in, k.es_sigma * (ts2 * ts2));
-  const double Qn_LW = d.LW_in - LW_out;
+  const double LW_in = d.get(kD_LWin);
+  const double LW_out = fma(k.one_m_es, LW_in, k.es_sigma * (ts2 * ts2));
+  const double Qn_LW = LW_in - LW_out;
   const double Q_sum = ((Qn_SW + Qn_LW) + Qh) + Qe;
   // -- snow: update_snow_meltrate :1364-1368, enforce_max_snow_meltrate :1465
   const double previous_swe = h_swe;                                            // :1571
@@ -416,7 +427,7 @@ __device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, Cel
   SM = div3600(nmin(R(__dmul_rn(SM, kLit.c3600)), R(h_swe))).v;
   h_swe = relu(R(__dsub_rn(h_swe, __dmul_rn(__dmul_rn(SM, dt), kLit.c3600)))).v;
   // -- update_snowfall_cold_content :1533-1537
-  if (P_snow > 0.0) Eccs = relu(R((Eccs + d.ccs) - E_in)).v;
+  if (P_snow > 0.0) Eccs = relu(R((Eccs + d.get(kD_ccs)) - E_in)).v;
   // -- update_ice_meltrate :1418-1428 (NEW h_swe, OLD h_ice), enforce_max_ice_meltrate :1473-1480
   double IM = (relu(R(E_in - Ecci)).v * k.inv_dt) * k.inv_rho_lf;
   IM = ((h_swe == 0.0) && (previous_swe == 0.0)) ? IM : 0.0;
@@ -436,12 +447,12 @@ __device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, Cel
 
   st.h_snow = h_snow; st.h_swe = h_swe; st.h_ice = h_ice; st.h_iwe = h_iwe;
   st.eccs = Eccs; st.ecci = Ecci; st.albedo = albedo; st.n_days = n;
-  o.SM = SM; o.IM = IM; o.M_total = M_total; o.RH = d.RH;
+  o.SM = SM; o.IM = IM; o.M_total = M_total; o.RH = d.get(kD_RH);
   // intermediates: only read when a caller records them (dead code otherwise)
-  const double e_sat_surf = warm ? (kLit.esat0 * 1.0) * 10.0 : d.es_dew;
-  o.p0 = d.p0; o.e_sat_air = d.e_sat_air; o.e_air = d.e_air; o.T_dew = T_dew; o.T_surf = T_surf; o.e_sat_surf = e_sat_surf;
-  o.Ri = fm::div_fast(top, bot); o.Dn = fm::div_fast(uk2, LL); o.Dh = Dh; o.Qh = Qh; o.W_p = d.W_p;
-  o.e_surf = d.RH * e_sat_surf; o.Qe = Qe; o.th = d.th; o.Qn_SW = Qn_SW; o.em_air = d.em_air; o.Qn_LW = Qn_LW;
+  const double e_sat_surf = warm ? (kLit.esat0 * 1.0) * 10.0 : d.get(kD_esdew);
+  o.p0 = d.get(kD_p0); o.e_sat_air = d.get(kD_esat_air); o.e_air = d.get(kD_eair); o.T_dew = T_dew; o.T_surf = T_surf; o.e_sat_surf = e_sat_surf;
+  o.Ri = fm::div_fast(top, bot); o.Dn = fm::div_fast(uk2, LL); o.Dh = Dh; o.Qh = Qh; o.W_p = d.get(kD_Wp);
+  o.e_surf = d.get(kD_RH) * e_sat_surf; o.Qe = Qe; o.th = d.get(kD_th); o.Qn_SW = Qn_SW; o.em_air = d.get(kD_emair); o.Qn_LW = Qn_LW;
   o.Q_sum = Q_sum; o.P_rain = P_rain; o.P_snow = P_snow;
 }
 

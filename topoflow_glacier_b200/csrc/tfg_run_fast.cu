@@ -1,6 +1,12 @@
 // float64 with algebraic shortcuts and written-out FMAs (TFG_F64_FAST)
-#ifndef TFG_PIPELINE   // 1: experimental software-pipelined time loop (tfg_pipe.cuh, needs -DTFG_SPLIT_STEP=1 for bit-identical
-#define TFG_PIPELINE 0 //    results across routes; measured slower); 0: single-stream loop of tfg_run.cuh (default)
+#ifndef TFG_WS         // 1: experimental warp-specialised producer / consumer kernel (tfg_ws.cuh) for fused launches: bit-identical
+#define TFG_WS 0       //    to the split single-stream kernel, measured slower (profiles/r2_experiments.md); 0 = default
+#endif
+#if TFG_WS && !defined(TFG_SPLIT_STEP)
+#define TFG_SPLIT_STEP 1   // every route of the fast mode then evaluates lean_forcing + lean_state: bit-identical results
+#endif
+#ifndef TFG_PIPELINE   // 1: experimental software-pipelined time loop (tfg_pipe.cuh, needs -DTFG_SPLIT_STEP=1; measured slower)
+#define TFG_PIPELINE 0
 #endif
 #ifdef TFG_LEAN_W2
 // Experimental two-cells-per-thread kernel with 128-bit forcing / state / window access (tfg_lean.cuh).  Bit-identical
@@ -9,15 +15,18 @@
 #include "tfg_lean.cuh"
 #else
 #include "tfg_pipe.cuh"
+#include "tfg_ws.cuh"
 #endif
 namespace tfg {
 cudaError_t launch_run_fast(const RunParams<double>& p, bool rec, bool agg, bool vol, cudaStream_t stream) {
 #ifdef TFG_LEAN_W2
   return launch_run_lean(p, rec, agg, vol, stream);
 #else
-  // one-step launches re-sum the snowfall window exactly (the literal update()), TMA staging is an option of the
-  // single-stream kernel; both evaluate the same two device functions, so results do not depend on the route
-  if (TFG_PIPELINE && !p.exact_ring && !p.use_tma) return launch_run_pipe(p, rec, agg, vol, stream);
+  // Recording launches, one-step launches (exact window re-sum: the literal update()), TMA staging and SATTERLUND
+  // configurations stay with the single-stream kernel; all routes evaluate the same device functions.
+  const bool fused = !p.exact_ring && !p.use_tma;
+  if (TFG_WS && fused && !rec && !p.k.satterlund && p.n_steps >= 2) return launch_run_ws(p, agg, vol, stream);
+  if (TFG_PIPELINE && fused) return launch_run_pipe(p, rec, agg, vol, stream);
   return launch_run<FastF64>(p, rec, agg, vol, stream);
 #endif
 }
