@@ -728,3 +728,35 @@ def test_packed_int16_forcing_equals_host_unpack(mode, cuda_device):
     else:
         assert np.array_equal(got, want.astype(np.float32))
     eng.close()
+
+
+def test_netcdf_file_to_packed_streamer_to_kernel(tmp_path, cuda_device):
+    """A NetCDF forcing file with int16-packed variables (scale_factor / add_offset) goes to the device UNCHANGED
+    (12 B per cell-step), is unpacked and converted there, and drives the fused kernel: the result equals the oracle run
+    on the host statement of the same unpacking (`unpack_forcing` -> `convert_on_host`) within the float64 tolerance."""
+    import pandas as pd
+    import torch
+
+    from topoflow_glacier_b200.forcing import (ForcingStreamer, convert_on_host, read_forcing_csv, read_forcing_netcdf,
+                                                 unpack_forcing, write_forcing_netcdf)
+
+    root = GOLDEN.parent.parent
+    case = load_case("cats288")
+    csv = root / "tests" / "data" / "sample-cat-3062920.csv"
+    raw = read_forcing_csv(csv)
+    when = pd.DatetimeIndex(pd.to_datetime(pd.read_csv(csv)["Time"]))
+    nc = tmp_path / "cats.nc"
+    write_forcing_netcdf(nc, when, np.repeat(raw[:, :, None], case["N"], axis=2))
+    packed, packing = read_forcing_netcdf(nc)
+    assert packed.dtype == np.int16 and packed.shape == (288, 6, case["N"])
+    forcing = convert_on_host(unpack_forcing(packed, packing))
+    want = make_oracle(dict(case, forcing=forcing), strict_pow=True).run(forcing, record=("M_total", "h_swe", "h_iwe", "Q_sum"))
+    eng = make_engine(case, mode="f64_fast")
+    st = ForcingStreamer(eng, chunk_steps=100, raw_dtype="int16", packing=packing)
+    parts = [eng.run(c, c.shape[0], record=("M_total", "h_swe", "h_iwe", "Q_sum")) for c in st.chunks(packed)]
+    assert st.h2d_bytes == packed.size * 2
+    for k in want:
+        got = torch.cat([pp[k] for pp in parts]).cpu().numpy()
+        ok, ratio, dabs, drel = err_report(got, want[k], ATOL[k])
+        assert ok, (k, ratio, dabs, drel)
+    eng.close()
