@@ -34,3 +34,11 @@ extern "C" void mc_log_tab_2(const double* x, const double* y, double* out, long
 extern "C" void mc_rcp3_3(const double* x, const double* y, double* out, long n) {
   for (long i = 0; i + 2 < n; i += 3) { const double a[3] = {x[i], x[i + 1], x[i + 2]}; double r[3]; rcp3_n<3>(a, r); out[i] = r[0]; out[i + 1] = r[1]; out[i + 2] = r[2]; }
 }
+// the fused exp pair + 7th root must return exactly what the separate routines return
+extern "C" void mc_exp2_root7(const double* x, const double* y, double* out, long n) {
+  for (long i = 0; i + 2 < n; i += 3) {
+    const double a[2] = {x[i], x[i + 1]}; double r[2], r7;
+    exp_tab2_root7(a, r, y[i + 2], r7);
+    out[i] = r[0]; out[i + 1] = r[1]; out[i + 2] = r7;
+  }
+}

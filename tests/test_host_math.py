@@ -130,6 +130,19 @@ def test_table_driven_wet_bulb_and_air_mass(lib):
     assert rel[c > 0.05].max() < 4e-15, rel[c > 0.05].max()
 
 
+def test_fused_exp_pair_and_seventh_root_equal_separate_routines(lib):
+    rng = np.random.default_rng(11)
+    n = 30000
+    x = rng.uniform(-8, 3, n)
+    y = 10.0 ** rng.uniform(-4, 0, n)          # argument of the 7th root: (e_air / 10) / T_K ~ 1e-3
+    got = call(lib, "mc_exp2_root7", x, y)
+    e = call(lib, "mc_exp_tab", x)
+    r = call(lib, "mc_root7", y, np.ones(n))
+    idx = np.arange(n - n % 3).reshape(-1, 3)
+    assert np.array_equal(got[idx[:, 0]], e[idx[:, 0]]) and np.array_equal(got[idx[:, 1]], e[idx[:, 1]])
+    assert np.array_equal(got[idx[:, 2]], r[idx[:, 2]])
+
+
 def test_seventh_root(lib):
     """x**(1/7) by one Householder step from a float32 seed: <= ~8 ulp with the seed's relative error up to 3e-6
     (MUFU lg2/ex2 deliver ~4e-7)."""

@@ -328,6 +328,54 @@ TFG_HD double root7(double x, float seed_scale = 1.0f) {
   return x * (v4 * v2);
 }
 
+// exp_tab_n<2> and root7 in one pass, stage by stage: the 7th root is a serial chain of twelve multiplications behind two
+// MUFU round trips; evaluated beside the two exponentials its latency is filled with their work.  Same operations per
+// value as the separate routines (bit-identical results).
+TFG_HD void exp_tab2_root7(const double (&x)[2], double (&y)[2], double xr, double& r7) {
+  float w0f;
+#if defined(__CUDA_ARCH__)
+  asm("{ .reg .f32 l; lg2.approx.ftz.f32 l, %1; mul.f32 l, l, 0fBE124925; ex2.approx.ftz.f32 %0, l; }" : "=f"(w0f) : "f"((float)xr));
+#else
+  w0f = exp2f(log2f((float)xr) * (-1.0f / 7.0f));
+#endif
+  double t[2], fn[2], r[2], T[2], r2[2], a[2], b[2];
+  int k[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) t[i] = fma(x[i], kML.exp_scale, 6755399441055744.0);
+  const double w0 = (double)w0f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { k[i] = lo32(t[i]); fn[i] = t[i] - 6755399441055744.0; }
+  const double w2 = w0 * w0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { r[i] = fma(fn[i], kML.exp_nl2h, x[i]); T[i] = TFG_EXPTAB(k[i] & 63); }
+  const double w4 = w2 * w2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) r[i] = fma(fn[i], kML.exp_nl2l, r[i]);
+  const double w6 = w4 * w2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    r2[i] = r[i] * r[i];
+    a[i] = fma(r[i], TFG_COEF(kExpTQ, 2), TFG_COEF(kExpTQ, 3));
+    b[i] = fma(r[i], TFG_COEF(kExpTQ, 0), TFG_COEF(kExpTQ, 1));
+  }
+  const double w7 = w6 * w0;
+  const double e = fma(-xr, w7, 1.0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) a[i] = fma(r2[i], b[i], a[i]);
+  const double u = e * fma(e, kML.r7_c2, kML.r7_c1);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) a[i] = fma(r2[i], a[i], r[i]);
+  const double w1 = fma(w0, u, w0);
+  const double v2 = w1 * w1;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double v = fma(T[i], a[i], T[i]);
+    y[i] = mk64(hi32(v) + ((k[i] >> 6) << 20), lo32(v));
+  }
+  const double v4 = v2 * v2;
+  r7 = xr * (v4 * v2);
+}
+
 // asin(x) for 0 <= x <= 1 (values slightly above 1 are clamped)
 TFG_HD double asin01(double x) {
   const bool big = x > 0.5;

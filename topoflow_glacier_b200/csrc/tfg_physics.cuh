@@ -23,6 +23,12 @@ static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.1
 #ifndef TFG_SPLIT_STEP
 #define TFG_SPLIT_STEP 0
 #endif
+#ifndef TFG_FUSE_ROOT7   // experiment: Brutsaert's 7th root evaluated beside the W_p / e_sat(T_surf) exponentials (fm::exp_tab2_root7);
+#define TFG_FUSE_ROOT7 0 // bit-identical, measured slower (28.5 vs 30.0 G: longer live ranges at the register limit)
+#endif
+#ifndef TFG_REUSE_COSZ   // fast float64: K_h = I_sc E0 max(cos Z, 0) reuses cos Z (the same fused multiply-add, bit for bit)
+#define TFG_REUSE_COSZ 1
+#endif
 #ifndef TFG_WETBULB_TABLE   // fast float64: Stull wet bulb from the tables of tfg_math.cuh (0: closed form, A/B runs)
 #define TFG_WETBULB_TABLE 1
 #endif
@@ -234,7 +240,10 @@ __device__ __forceinline__ Num<P> clear_sky(const Consts<typename P::raw>& k, co
   const R gam_s = (R(1.0) - e_gam) + R(k.dust);
   // ET_Radiation_Flux solar_funcs.py:391-412 ; ET_Radiation_Flux_Slope :866-887
   const R isc_e0(tr.isc_e0);
-  const R K_h = relu(isc_e0 * fmadd(cos_d * R(s.get(kSCosLat)), c_wt, sin_d * R(s.get(kSSinLat))));
+  // (cos_d cos_lat) cos(wt) + sin_d sin_lat is cos Z itself: the products commute exactly, so the lean path reuses it
+  R K_h;
+  if constexpr (P::lean && TFG_REUSE_COSZ) K_h = relu(isc_e0 * cosZ);
+  else K_h = relu(isc_e0 * fmadd(cos_d * R(s.get(kSCosLat)), c_wt, sin_d * R(s.get(kSSinLat))));
   const R K_s = relu(isc_e0 * fmadd(cos_d * R(s.get(kSCosEq)), c_u, R(s.get(kSSinEq)) * sin_d));
   const R half_gam = R(0.5) * gam_s;
   const R K_dif = half_gam * K_h;                            // :667
@@ -498,6 +507,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     s.set(kSVolPS, fmadd(P_snow * da, dt, R(s.get(kSVolPS))).v);
   }
   R p0, e_sat_air, e_air, RH, T_dew, T_surf, e_sat_surf, dT, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, rTK;
+  double root7_pre = 0.0;   // x**(1/7) of update_em_air, evaluated early beside two exponentials (lean, TFG_FUSE_ROOT7)
   if constexpr (P::lean) {
     // Same quantities with 7 instead of 12 divisions: 1/T_K is shared, 1/p0 and RH come from exp(-x) instead of
     // dividing by exp(x), and the aerodynamic block (:640-733) collapses into one quotient:
@@ -543,7 +553,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // -- W_p = 1.12 exp(0.0614 T_dew) (:919-920) and e_sat(T_surf) (:784-802)
     const double ex2b[2] = {(LIT(wp_b, 0.0614) * T_dew).v, ((LIT(mag_a, 17.3) * T_surf) * R(rc2[0])).v};
     double ey2b[2];
-    fm::exp_tab_n<2>(ex2b, ey2b);
+    if constexpr (TFG_FUSE_ROOT7) fm::exp_tab2_root7(ex2b, ey2b, ((e_air * LIT(c01, 0.1)) * rTK).v, root7_pre);
+    else fm::exp_tab_n<2>(ex2b, ey2b);
     W_p = LIT(wp_a, 1.12) * R(ey2b[0]);
     e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
     Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
@@ -619,7 +630,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     R x;
     if constexpr (P::lean) x = (e_air * LIT(c01, 0.1)) * rTK; else x = divk(e_air, 10.0) / T_K;
     R term1;
-    if constexpr (P::lean) term1 = R(k.emis_a) * R(fm::root7(x.v));   // x > 0 on the sane path
+    if constexpr (P::lean && TFG_FUSE_ROOT7) term1 = R(k.emis_a) * R(root7_pre);
+    else if constexpr (P::lean) term1 = R(k.emis_a) * R(fm::root7(x.v));   // x > 0 on the sane path
     else term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
     em_air = fmadd(term1, R(k.emis_b), R(k.canopy));
   } else {
