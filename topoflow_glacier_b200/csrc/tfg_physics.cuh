@@ -26,6 +26,9 @@ static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.1
 #ifndef TFG_FUSE_ROOT7   // experiment: Brutsaert's 7th root evaluated beside the W_p / e_sat(T_surf) exponentials (fm::exp_tab2_root7);
 #define TFG_FUSE_ROOT7 0 // bit-identical, measured slower (28.5 vs 30.0 G: longer live ranges at the register limit)
 #endif
+#ifndef TFG_FOLD_CONSTS  // fast float64: constant factors folded (a_elev/R* per launch, rho_air Lv 0.622/p0c, 0.611*10): -4 FP64 per step
+#define TFG_FOLD_CONSTS 1
+#endif
 #ifndef TFG_REUSE_COSZ   // fast float64: K_h = I_sc E0 max(cos Z, 0) reuses cos Z (the same fused multiply-add, bit for bit)
 #define TFG_REUSE_COSZ 1
 #endif
@@ -109,7 +112,9 @@ __device__ __forceinline__ float balance64(float& h, float& lo, float gain, floa
 // SmemCell keeps them in shared memory, one column per thread, and reads a value where it is used: in registers
 // (RegCell) they pin ~44 registers for the whole time loop and hold the float64 kernels at 3 blocks per SM.
 enum { kSaElev, kSSinLat, kSCosLat, kSNegTanLat, kSSinEq, kSCosEq, kSNegTanEq, kSDlon, kSTNoon, kSDa, kSTrs,
-       kSCB, kSSB, kSCB2, kSSB2, kSVolP, kSVolPR, kSVolPS, kSVolSM, kSVolIM, kSPmax, kSCount };
+       kSCB, kSSB, kSCB2, kSSB2, kSVolP, kSVolPR, kSVolPS, kSVolSM, kSVolIM, kSPmax,
+       kSaElevR,   // fast float64 only: a_elev / R*, formed once per launch instead of once per step
+       kSCount };
 
 template <class raw>
 struct RegCell {
@@ -523,7 +528,10 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     const R e = (q * P_air) * R(rc3[1]);
     e_air = e * LIT(c001, 0.01);
     // -- exp(-M g elev / (R* T_K)) (:551-556), exp(-17.3 T/(T+237.3)); log(e_air/6.1121) (:892), the log law (:670)
-    const double ex2[2] = {(-((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK)).v, (-((LIT(mag_a, 17.3) * T_air) * R(rc3[2]))).v};
+    R ex_p0;
+    if constexpr (TFG_FOLD_CONSTS) ex_p0 = -(R(s.get(kSaElevR)) * rTK);
+    else ex_p0 = -((R(s.get(kSaElev)) * R(k.inv_rstar)) * rTK);
+    const double ex2[2] = {ex_p0.v, (-((LIT(mag_a, 17.3) * T_air) * R(rc3[2]))).v};
     const double lx2[2] = {(e_air * LIT(inv_dew_a, 0.1636098885816659)).v,
                            nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)).v};
     double ey2[2], ly2[2];
@@ -556,10 +564,14 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     if constexpr (TFG_FUSE_ROOT7) fm::exp_tab2_root7(ex2b, ey2b, ((e_air * LIT(c01, 0.1)) * rTK).v, root7_pre);
     else fm::exp_tab_n<2>(ex2b, ey2b);
     W_p = LIT(wp_a, 1.12) * R(ey2b[0]);
-    e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
+    if constexpr (TFG_FOLD_CONSTS) e_sat_surf = LIT(esat10, 6.11) * R(ey2b[1]);
+    else e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
     Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
     e_surf = RH * e_sat_surf;                                                                // :853
-    Qe = ((R(k.rho_lv_air) * Dh) * fnmadd(RH, e_sat_surf, e_air)) * (R(k.lhc) * inv_p0);     // :931-934
+    if constexpr (TFG_FOLD_CONSTS)                                                           // :931-934, constants folded into cq0
+      Qe = (Dh * fnmadd(RH, e_sat_surf, e_air)) * (R(ey2[0]) * R(k.cq0));
+    else
+      Qe = ((R(k.rho_lv_air) * Dh) * fnmadd(RH, e_sat_surf, e_air)) * (R(k.lhc) * inv_p0);
     // only read when a caller records them (dead code otherwise)
     p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
     e_sat_air = LIT(esat10, 6.11) / en;

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   s.set(kSNegTanEq, __ldg(p.neg_tan_eq + c)); s.set(kSDlon, __ldg(p.dlon + c)); s.set(kSTNoon, __ldg(p.t_noon + c));
   s.set(kSDa, __ldg(p.da_m2 + c)); s.set(kSTrs, __ldg(p.t_rs + c));
   s.set(kSCB, 0); s.set(kSSB, 0); s.set(kSCB2, 0); s.set(kSSB2, 0);
+  s.set(kSaElevR, (raw)(s.get(kSaElev) * p.k.inv_rstar));
   const R lon(__ldg(p.lon + c));
   const int tz = p.tz_idx ? (int)__ldg(p.tz_idx + c) : 0;
 
@@ -189,6 +190,10 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   s.set(kSVolPS, have_vol ? p.vol_PS[c] : 0); s.set(kSVolSM, have_vol ? p.vol_SM[c] : 0);
   s.set(kSVolIM, have_vol ? p.vol_IM[c] : 0); s.set(kSPmax, have_vol ? p.P_max[c] : 0);
 
+  // warps that hold no real cell at all (tail block only) stop here: every block-wide barrier is behind us
+  // (TMA staging, whose mbarriers count 128 arrivals, is only used when n_cells is a multiple of the block size)
+  const bool warp_has_cells = (int64_t)blockIdx.x * kBlock + (threadIdx.x & ~31) < p.n_cells;
+  if (!warp_has_cells) return;
   const int slots = p.ring_slots;
   int slot = (int)(p.step0 % slots);
   raw* ring = p.ring + c;
@@ -324,7 +329,12 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     R tot_now;
     auto window = [&](raw ring_new_raw) -> raw {
       const R ring_new(ring_new_raw);
-      if (active) *(kWalk ? ring_cur : ring + (int64_t)slot * N) = ring_new.v;  // np.roll(-1) + write of the newest slot, :1027-1033
+      // np.roll(-1) + write of the newest slot, :1027-1033.  Not predicated on `active` (which ptxas re-derives from
+      // S2R + 64-bit compares at every use): threads past the last cell replicate cell N-1 IN THE SAME WARP, in lockstep
+      // and with identical inputs, so they store the identical value at the same instant; warps without any real cell
+      // have left the kernel (see `warp_has_cells`), because a replica warp running a step ahead would overwrite a slot
+      // the real cell has not read yet
+      *(kWalk ? ring_cur : ring + (int64_t)slot * N) = ring_new.v;
       if (exact) {
         tot_now = window_sum_exact<P>(ring, N, slots, slot);
       } else {
