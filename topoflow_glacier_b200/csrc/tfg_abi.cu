@@ -141,6 +141,10 @@ tfg::RunParams<raw> make_params(const tfg_ctx* x, const void* forcing, int64_t s
     p.rows[t] = tfg::TimeRow<raw>{(raw)r[0], (raw)r[1], (raw)r[2], (raw)r[3], (raw)r[4], (raw)r[5], (raw)r[6], (raw)r[7]};
     for (int z = 0; z < x->n_tz; ++z) p.gmt[t * x->n_tz + z] = (raw)x->h_gmt[(size_t)(step0 + t) * x->n_tz + z];
   }
+  p.gmt_varies = 0;
+  for (int32_t t = 1; t < n_steps && !p.gmt_varies; ++t)
+    for (int z = 0; z < x->n_tz; ++z)
+      if (!(p.gmt[t * x->n_tz + z] == p.gmt[z])) p.gmt_varies = 1;   // also true for NaN offsets
   p.record = static_cast<raw*>(record);
   p.record_mask = mask;
   p.n_rec = __builtin_popcountll(mask);

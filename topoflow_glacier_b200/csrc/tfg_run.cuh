@@ -26,6 +26,9 @@ namespace tfg {
 #ifndef TFG_CPASYNC  // 1: next-step forcings staged in shared memory by cp.async instead of register prefetches (measured slower)
 #define TFG_CPASYNC 0
 #endif
+#ifndef TFG_ZONE_ONCE  // 1: a launch without a DST switch sets each cell's zone terms once instead of comparing the offset every step
+#define TFG_ZONE_ONCE 1
+#endif
 #ifndef TFG_MIN_BLOCKS_LEAN  // fast float64 kernel: cell constants in shared memory, clock rows in the parameter block -> 96 registers
 #define TFG_MIN_BLOCKS_LEAN 5
 #endif
@@ -36,6 +39,7 @@ template <class raw>
 struct RunParams {
   int64_t n_cells, step0;
   int32_t n_steps, ring_slots, n_tz, exact_ring, use_tma;
+  int32_t gmt_varies;  // 0: every zone keeps its UTC offset over this launch (no DST switch inside): the zone is set once
   const raw* forcing;
   const int32_t* forcing_col;  // optional: cell -> column of the forcing block (cells of one catchment share a column)
   int64_t n_cols;              // columns of the forcing block (= n_cells without a map)
@@ -286,6 +290,10 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   };
   raw gmt_prev = __longlong_as_double(0x7ff8000000000000ll);  // NaN: the first step always sets the zone
 
+  if (TFG_ZONE_ONCE && !p.gmt_varies) {  // the common case: one UTC offset per zone for the whole launch
+    gmt_prev = p.gmt[tz];
+    set_zone(gmt_prev);
+  }
   bool statics_sane = true, state_ok = true;
   auto finite = [](raw v) { return ((unsigned)__double2hiint((double)v) & 0x7ff00000u) != 0x7ff00000u; };
   if constexpr (P::lean) {  // finite tables, |a_elev| < 2e5 (|elev| < 700 km), finite carried state
@@ -317,10 +325,12 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       if (t + 1 < p.n_steps) stage_forcing(t + 1);
     }
     const TimeRow<raw>& row = p.rows[t];
-    const raw gmt = p.gmt[t * p.n_tz + tz];
-    if (!(gmt == gmt_prev)) {  // first step, or DST switch (the offset is piece-wise constant in time)
-      gmt_prev = gmt;
-      set_zone(gmt);
+    if (!TFG_ZONE_ONCE || p.gmt_varies) {  // a DST switch falls into this launch (twice a year): follow the offset step by step
+      const raw gmt = p.gmt[t * p.n_tz + tz];
+      if (!(gmt == gmt_prev)) {  // the offset is piece-wise constant in time
+        gmt_prev = gmt;
+        set_zone(gmt);
+      }
     }
     const bool wrap = (slot + 1 == slots);
     const int slot_next = wrap ? 0 : slot + 1;
