@@ -334,6 +334,7 @@ int tfg_set_constants(tfg_ctx* x, const tfg_constants* c) {
 int tfg_bind_static(tfg_ctx* x, int64_t n_cells, const tfg_statics* s) {
   if (!x || !s) return fail("tfg_bind_static: NULL argument");
   if (n_cells <= 0) return fail("tfg_bind_static: n_cells must be > 0");
+  if (n_cells >= (int64_t(1) << 31)) return fail("tfg_bind_static: at most 2^31 - 1 cells per shard (a cell's state alone is ~1 KB: 180 GB of HBM hold < 2^28)");
   const void* req[] = {s->a_elev, s->sin_lat, s->cos_lat, s->neg_tan_lat, s->lon, s->sin_lat_eq, s->cos_lat_eq,
                        s->neg_tan_lat_eq, s->dlon, s->t_noon, s->da_m2, s->t_rain_snow};
   for (const void* p : req)

@@ -23,6 +23,12 @@ static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.1
 #ifndef TFG_SPLIT_STEP
 #define TFG_SPLIT_STEP 0
 #endif
+#ifndef TFG_ALBEDO_EARLY  // fast float64 step: the albedo-ageing exponential (:1042-1048) is evaluated beside the W_p / e_sat(T_surf)
+#define TFG_ALBEDO_EARLY 1 // exponentials (one group of three shares table index arithmetic and coefficients); bit-identical, +0.7 %
+#endif
+#ifndef TFG_EXP5   // experiment: all five exponentials of the met block in one group
+#define TFG_EXP5 0
+#endif
 #ifndef TFG_FUSE_ROOT7   // experiment: Brutsaert's 7th root evaluated beside the W_p / e_sat(T_surf) exponentials (fm::exp_tab2_root7);
 #define TFG_FUSE_ROOT7 0 // bit-identical, measured slower (28.5 vs 30.0 G: longer live ranges at the register limit)
 #endif
@@ -512,6 +518,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     s.set(kSVolPS, fmadd(P_snow * da, dt, R(s.get(kSVolPS))).v);
   }
   R p0, e_sat_air, e_air, RH, T_dew, T_surf, e_sat_surf, dT, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, rTK;
+  R n_early, tot_early, alb_exp;   // lean + TFG_ALBEDO_EARLY: days since snowfall, window sum, exp(-n r)
   double root7_pre = 0.0;   // x**(1/7) of update_em_air, evaluated early beside two exponentials (lean, TFG_FUSE_ROOT7)
   if constexpr (P::lean) {
     // Same quantities with 7 instead of 12 divisions: 1/T_K is shared, 1/p0 and RH come from exp(-x) instead of
@@ -535,11 +542,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     const double lx2[2] = {(e_air * LIT(inv_dew_a, 0.1636098885816659)).v,
                            nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)).v};
     double ey2[2], ly2[2];
-    fm::exp_tab_n<2>(ex2, ey2);
+    if constexpr (!(TFG_EXP5 && TFG_ALBEDO_EARLY)) fm::exp_tab_n<2>(ex2, ey2);
     fm::log_tab_n<2>(lx2, ly2);
-    const R inv_p0 = R(ey2[0]) * R(k.inv_p0c);
-    const R en(ey2[1]);
-    RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                                 // e_air / (6.11 exp(t1)), :838
     const R log_term(ly2[0]), L(ly2[1]);
     T_dew = (LIT(dew_c, 257.14) * log_term) * R(fm::rcp3((LIT(dew_b, 18.678) - log_term).v));
     const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
@@ -561,8 +565,27 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // -- W_p = 1.12 exp(0.0614 T_dew) (:919-920) and e_sat(T_surf) (:784-802)
     const double ex2b[2] = {(LIT(wp_b, 0.0614) * T_dew).v, ((LIT(mag_a, 17.3) * T_surf) * R(rc2[0])).v};
     double ey2b[2];
-    if constexpr (TFG_FUSE_ROOT7) fm::exp_tab2_root7(ex2b, ey2b, ((e_air * LIT(c01, 0.1)) * rTK).v, root7_pre);
+    if constexpr (TFG_ALBEDO_EARLY) {
+      const R r = sel(T_air > 0.0, LIT(alb_r1, 0.12), LIT(alb_r0, 0.05));
+      const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
+      tot_early = R(window_sum(ring_new.v));                     // :1027-1037
+      n_early = sel(tot_early < LIT(snow_thr, 0.03), R(st.n_days) + R(k.days_per_dt), R(0.0));
+      if constexpr (TFG_EXP5) {
+        const double ex5[5] = {ex2[0], ex2[1], ex2b[0], ex2b[1], ((-n_early) * r).v};
+        double ey5[5];
+        fm::exp_tab_n<5>(ex5, ey5);
+        ey2[0] = ey5[0]; ey2[1] = ey5[1]; ey2b[0] = ey5[2]; ey2b[1] = ey5[3]; alb_exp = R(ey5[4]);
+      } else {
+        const double ex3[3] = {ex2b[0], ex2b[1], ((-n_early) * r).v};
+        double ey3[3];
+        fm::exp_tab_n<3>(ex3, ey3);
+        ey2b[0] = ey3[0]; ey2b[1] = ey3[1]; alb_exp = R(ey3[2]);
+      }
+    } else if constexpr (TFG_FUSE_ROOT7) fm::exp_tab2_root7(ex2b, ey2b, ((e_air * LIT(c01, 0.1)) * rTK).v, root7_pre);
     else fm::exp_tab_n<2>(ex2b, ey2b);
+    const R inv_p0 = R(ey2[0]) * R(k.inv_p0c);
+    const R en(ey2[1]);
+    RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);                                 // e_air / (6.11 exp(t1)), :838
     W_p = LIT(wp_a, 1.12) * R(ey2b[0]);
     if constexpr (TFG_FOLD_CONSTS) e_sat_surf = LIT(esat10, 6.11) * R(ey2b[1]);
     else e_sat_surf = (LIT(esat0, 0.611) * R(ey2b[1])) * 10.0;
@@ -618,19 +641,24 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R solar_noon = (LIT(c12, 12.0) + LC) + R(tr.TE);
   const R th = R(tr.clock_hour) - solar_noon;
   // ---- update_albedo("aging") :1023-1059
-  const R r = sel(T_air > 0.0, LIT(alb_r1, 0.12), LIT(alb_r0, 0.05));
-  const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
-  const R tot(window_sum(ring_new.v));                       // :1027-1037
-  R n(st.n_days);
-  const R thr = LIT(snow_thr, 0.03);
-  if constexpr (P::strict) {
-    n = sel(tot >= thr, R(0.0), n);                         // :1040
-    n = sel(tot < thr, n + R(k.days_per_dt), n);            // :1041
+  R n, tot, albedo(st.albedo);
+  if constexpr (P::lean && TFG_ALBEDO_EARLY) {
+    n = n_early; tot = tot_early;
+    albedo = sel(h_snow > 0.0, fmadd(LIT(alb_k, 0.44), alb_exp, LIT(alb_0, 0.4)), albedo);
   } else {
-    n = sel(tot < thr, n + R(k.days_per_dt), R(0.0));       // tot is finite on the sane path
+    const R r = sel(T_air > 0.0, LIT(alb_r1, 0.12), LIT(alb_r0, 0.05));
+    const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
+    tot = R(window_sum(ring_new.v));                           // :1027-1037
+    n = R(st.n_days);
+    const R thr = LIT(snow_thr, 0.03);
+    if constexpr (P::strict) {
+      n = sel(tot >= thr, R(0.0), n);                         // :1040
+      n = sel(tot < thr, n + R(k.days_per_dt), n);            // :1041
+    } else {
+      n = sel(tot < thr, n + R(k.days_per_dt), R(0.0));       // tot is finite on the sane path
+    }
+    if (h_snow > 0.0) albedo = fmadd(LIT(alb_k, 0.44), nexp((-n) * r), LIT(alb_0, 0.4));  // :1042-1048
   }
-  R albedo(st.albedo);
-  if (h_snow > 0.0) albedo = fmadd(LIT(alb_k, 0.44), nexp((-n) * r), LIT(alb_0, 0.4));  // :1042-1048
   if (h_snow == 0.0 && h_ice > 0.0) albedo = LIT(alb_ice, 0.3);         // :1049-1053
   if (h_snow == 0.0 && h_ice == 0.0) albedo = LIT(alb_bare, 0.15);       // :1054-1058
   // ---- update_net_shortwave_radiation :1122-1139

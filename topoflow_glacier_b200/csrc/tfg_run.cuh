@@ -26,6 +26,12 @@ namespace tfg {
 #ifndef TFG_CPASYNC  // 1: next-step forcings staged in shared memory by cp.async instead of register prefetches (measured slower)
 #define TFG_CPASYNC 0
 #endif
+#ifndef TFG_WALK_LEAN  // 1: the fast float64 kernel carries the window-slot pointer (as the float32 kernel does) instead of re-deriving it
+#define TFG_WALK_LEAN 0   // measured slower (30.6 vs 31.2 G): two more live registers at the 96-register limit
+#endif
+#ifndef TFG_DA_ZERO    // 1: replica lanes past the last cell carry area 0, so the basin sums need no `active` predicate
+#define TFG_DA_ZERO 1
+#endif
 #ifndef TFG_ZONE_ONCE  // 1: a launch without a DST switch sets each cell's zone terms once instead of comparing the offset every step
 #define TFG_ZONE_ONCE 1
 #endif
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   s.set(kSaElev, __ldg(p.a_elev + c)); s.set(kSSinLat, __ldg(p.sin_lat + c)); s.set(kSCosLat, __ldg(p.cos_lat + c));
   s.set(kSNegTanLat, __ldg(p.neg_tan_lat + c)); s.set(kSSinEq, __ldg(p.sin_eq + c)); s.set(kSCosEq, __ldg(p.cos_eq + c));
   s.set(kSNegTanEq, __ldg(p.neg_tan_eq + c)); s.set(kSDlon, __ldg(p.dlon + c)); s.set(kSTNoon, __ldg(p.t_noon + c));
-  s.set(kSDa, __ldg(p.da_m2 + c)); s.set(kSTrs, __ldg(p.t_rs + c));
+  s.set(kSDa, (TFG_DA_ZERO && !active) ? raw(0) : __ldg(p.da_m2 + c)); s.set(kSTrs, __ldg(p.t_rs + c));
   s.set(kSCB, 0); s.set(kSSB, 0); s.set(kSCB2, 0); s.set(kSSB2, 0);
   s.set(kSaElevR, (raw)(s.get(kSaElev) * p.k.inv_rstar));
   const R lon(__ldg(p.lon + c));
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
 
   // warps that hold no real cell at all (tail block only) stop here: every block-wide barrier is behind us
   // (TMA staging, whose mbarriers count 128 arrivals, is only used when n_cells is a multiple of the block size)
-  const bool warp_has_cells = (int64_t)blockIdx.x * kBlock + (threadIdx.x & ~31) < p.n_cells;
+  const bool warp_has_cells = (int64_t)blockIdx.x * kBlock + (threadIdx.x & ~31u) < p.n_cells;
   if (!warp_has_cells) return;
   const int slots = p.ring_slots;
   int slot = (int)(p.step0 % slots);
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
   // float32 kernel: the slot pointer walks through the window (no 64-bit multiply per step); the float64 kernels
   // are register-bound and recompute the address instead of carrying two more pointers
-  constexpr bool kWalk = P::f32;
+  constexpr bool kWalk = P::f32 || (P::lean && TFG_WALK_LEAN);
   raw* ring_cur = ring + (int64_t)slot * N;
   raw r_old = *ring_cur;
   R LC(0.0);
@@ -334,7 +340,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     }
     const bool wrap = (slot + 1 == slots);
     const int slot_next = wrap ? 0 : slot + 1;
-    raw* ring_next = kWalk ? (wrap ? ring : ring_cur + N) : ring + (int64_t)slot_next * N;
+    raw* ring_next;
+    if constexpr (kWalk) ring_next = ring_cur + (wrap ? -(int64_t)(slots - 1) * N : N);  // a warp-uniform stride: no cell index needed
+    else ring_next = ring + (int64_t)slot_next * N;
     raw r_next = 0;
     R tot_now;
     auto window = [&](raw ring_new_raw) -> raw {
@@ -443,9 +451,10 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         // area-weighted basin sums (np.sum sites :567-568,:1486-1494 and the driver's `* da_m2`):
         // warp-shuffle tree when the warp sits inside one basin, one RED per warp and quantity
         const double da = (double)s.get(kSDa);
-        double v0 = active ? (double)o.M_total * da : 0.0;
-        double v1 = active ? (double)st.h_swe * da : 0.0;
-        double v2 = active ? (double)st.h_iwe * da : 0.0;
+        const bool counted = TFG_DA_ZERO || active;
+        double v0 = counted ? (double)o.M_total * da : 0.0;
+        double v1 = counted ? (double)st.h_swe * da : 0.0;
+        double v2 = counted ? (double)st.h_iwe * da : 0.0;
         const int64_t entry = ((int64_t)t * p.n_basin + basin) * TFG_N_AGG;
         double* dst = static_cast<double*>(p.basin_agg) + entry;
         long long* acc = static_cast<long long*>(p.basin_agg) + 2 * entry;
