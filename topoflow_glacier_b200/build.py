@@ -54,7 +54,7 @@ def is_current() -> bool:
     return LIB.exists() and stamp.exists() and stamp.read_text().strip() == source_digest()
 
 
-def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None, extra=()) -> Path:
     """Compile every CUDA source for sm_100a and link libtfglacier.so; returns its path.
 
     ``defines`` / ``out`` build an experimental variant next to the stock library (tuning sweeps).
@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: Path | No
 
     def compile_one(src: str) -> Path:
         obj = objdir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *[f"-D{d}" for d in defines], "-I", str(INCLUDE), "-c",
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *[f"-D{d}" for d in defines], *extra, "-I", str(INCLUDE), "-c",
                str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -95,4 +95,5 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: Path | No
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    extra = [a for a in sys.argv[1:] if a.startswith("-X")]   # e.g. -Xptxas=--register-usage-level=7 (tuning sweeps)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None, extra=extra))
