@@ -624,6 +624,15 @@ def run_gpu_arm(args):
                   "d2h_bytes_per_step": out_host[0].numel() * out_host[0].element_size() + agg_sh[0].numel() * 8,
                   "timesteps_per_step": Ts, "forcing_columns": N_BASIN, "out_dtype": args.e2e_out,
                   "path": "as e2e, one float32 forcing series per basin (tfg_bind_forcing_map) instead of one per cell"}
+        # the launch alone on device-resident columns (column-term pass + melt kernel), CUDA events around each launch
+        fcol = forcing[:Ts, :, :N_BASIN].contiguous()
+        for _ in range(2):
+            eng.run(fcol, Ts, basin_agg=zero_agg())
+        k_sh, _ = time_launches(eng, fcol, Ts, zero_agg, reduce_agg, 3, world, dev)
+        shared["launch_ms"] = k_sh
+        shared["launch_cell_steps_per_s_per_gpu"] = n_cells * Ts / (k_sh * 1e-3)
+        shared["column_terms"] = bool(eng.column_term_launches > 0)   # TFG_OPT_COLUMN_TERMS (env TFG_COLUMN_TERMS=0 switches it off)
+        del fcol
         eng.set_forcing_map(None)
         del streamer2, agg_s
 

@@ -760,3 +760,51 @@ def test_netcdf_file_to_packed_streamer_to_kernel(tmp_path, cuda_device):
         ok, ratio, dabs, drel = err_report(got, want[k], ATOL[k])
         assert ok, (k, ratio, dabs, drel)
     eng.close()
+
+
+def test_column_terms_pass_is_bit_identical_and_taken(cuda_device):
+    """TFG_OPT_COLUMN_TERMS: with a forcing map of few columns the fast float64 engine evaluates the forcing-only part
+    of update() once per column and timestep (column_terms_kernel) -- every recorded quantity, the state, the snowfall
+    window, the diagnostic integrals and the exact basin sums must equal the per-cell evaluation bit for bit, also where
+    a column holds missing or absurd forcing (those cell-steps take the strict step from the raw values in both)."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200 import _lib
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.sharding import BasinAggregates
+
+    N, M, T = 3000, 24, 150                                        # 150 steps: two launches (128 + 22)
+    statics, _ = bench.synthetic_host_sample(N, 1, seed=11)
+    _, fcols = bench.synthetic_host_sample(M, T, seed=12)          # [T, 5, M]
+    fcols = np.ascontiguousarray(fcols)
+    fcols[17, 1, 3] = np.nan                                       # missing air temperature in column 3
+    fcols[40:44, 4, 5] = 0.0                                       # calm
+    fcols[60, 2, 7] = 5.0e6                                        # absurd pressure: strict step
+    fcols[61, 3, 7] = 0.5                                          # absurd humidity
+    fcols[90, 0, 9] = -1.0e-3                                      # negative precipitation
+    col = (np.arange(N) * M // N).astype(np.int32)                 # contiguous catchments ...
+    col[::7] = np.random.default_rng(5).integers(0, M, col[::7].size)   # ... with foreign cells inside the warps
+    basin = (np.arange(N) // 100).astype(np.int32)
+    kw = dict(zones=[-8.0], mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M,
+              basin_id=basin, n_basin=30)
+    f = torch.as_tensor(fcols).to(cuda_device, torch.float64).contiguous()
+    out = {}
+    for on in (True, False):
+        e = MeltEngine(statics, default_constants(), "2013020100", column_terms=on, **kw)
+        agg = BasinAggregates(T, 30, device=cuda_device, exponents=e.agg_exponents())
+        rec = e.run(f, record=_lib.REC_NAMES, basin_agg=agg.accumulator)
+        half = e.run(f[:T // 2].contiguous())                      # and a launch without recording / aggregates
+        torch.cuda.synchronize()
+        out[on] = (rec, e.state.clone(), e.ring.clone(), agg.accumulator.clone(), e.column_term_launches)
+        assert half == {}
+        e.close()
+    assert out[True][4] == 3 and out[False][4] == 0                # 2 + 1 launches took the pass
+    for name in _lib.REC_NAMES:
+        a, b = out[True][0][name], out[False][0][name]
+        assert torch.equal(a.view(torch.int64), b.view(torch.int64)), name   # bit patterns: NaN-poisoned cells included
+    for i in (1, 2):   # state (incl. the diagnostic integrals) and snowfall window
+        assert torch.equal(out[True][i].view(torch.int64), out[False][i].view(torch.int64))
+    assert torch.equal(out[True][3], out[False][3])                # exact basin sums and the left-out counter
+    assert torch.isnan(out[True][1]).any()                         # the missing value did poison its cells

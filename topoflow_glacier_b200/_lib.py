@@ -13,6 +13,7 @@ MODE_NAMES = {"f64": F64_STRICT, "f64_strict": F64_STRICT, "strict": F64_STRICT,
               "fast": F64_FAST, "f32": F32, "fp32": F32, "fp64": F64_STRICT}
 OPT_TMA_STAGING = 1
 OPT_EXACT_AGG = 2
+OPT_COLUMN_TERMS = 3
 N_FORCING = 5
 N_AGG = 3
 MAX_TZ = 8
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "tfg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "tfg_destroy": (None, [C.c_void_p]),
     "tfg_mode": (C.c_int, [C.c_void_p]),
+    "tfg_column_term_launches": (C.c_int64, [C.c_void_p]),
     "tfg_elem_size": (C.c_size_t, [C.c_void_p]),
     "tfg_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "tfg_set_constants": (C.c_int, [C.c_void_p, C.POINTER(Constants)]),

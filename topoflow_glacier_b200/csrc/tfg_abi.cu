@@ -50,6 +50,10 @@ struct tfg_ctx {
   void* win_carry = nullptr;             // tfg_bind_window_carry
   void* mass_lo = nullptr;               // tfg_bind_mass_residual
   int64_t n_cols = 0;
+  int column_terms = 1;                  // TFG_OPT_COLUMN_TERMS
+  double* col_terms = nullptr;           // [<= kMaxLaunchSteps][n_cols][16] scratch of the column-term pass (owned)
+  size_t col_terms_bytes = 0;
+  int64_t col_term_launches = 0;         // launches that went through the column-term pass (tfg_column_term_launches)
 };
 
 namespace {
@@ -309,16 +313,19 @@ int tfg_create(tfg_ctx** out, int device, int mode) {
 void tfg_destroy(tfg_ctx* x) {
   if (!x) return;
   cudaSetDevice(x->device);
+  if (x->col_terms) cudaFree(x->col_terms);
   delete x;
 }
 
 int tfg_mode(const tfg_ctx* x) { return x ? x->mode : -1; }
+int64_t tfg_column_term_launches(const tfg_ctx* x) { return x ? x->col_term_launches : -1; }
 size_t tfg_elem_size(const tfg_ctx* x) { return (x && x->mode == TFG_F32) ? 4 : 8; }
 
 int tfg_set_option(tfg_ctx* x, int option, int64_t value) {
   if (!x) return fail("tfg_set_option: NULL context");
   if (option == TFG_OPT_TMA_STAGING) { x->use_tma = value != 0; return 0; }
   if (option == TFG_OPT_EXACT_AGG) { x->exact_agg = value; return 0; }
+  if (option == TFG_OPT_COLUMN_TERMS) { x->column_terms = value != 0; return 0; }
   return fail("tfg_set_option: unknown option");
 }
 
@@ -419,7 +426,31 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
       e = tfg::launch_run_f32(make_params<float>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad), rec, agg, vol, s);
     } else {
       auto p = make_params<double>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad);
-      e = (x->mode == TFG_F64_STRICT) ? tfg::launch_run_strict(p, rec, agg, vol, s) : tfg::launch_run_fast(p, rec, agg, vol, s);
+      if (x->mode == TFG_F64_STRICT) {
+        e = tfg::launch_run_strict(p, rec, agg, vol, s);
+      } else {
+        // Forcing map with few columns per cell: the forcing-only part of the step is evaluated once per column and
+        // timestep (column_terms_kernel) and the melt kernel reads one line per step instead of redoing it per cell.
+        // Same device functions either way: results do not depend on this switch (test_column_terms_*).
+        const size_t need = (size_t)nt * (size_t)x->n_cols * tfg::kCtCount * sizeof(double);
+        if (x->column_terms && x->forcing_col && !x->use_tma && !x->c.satterlund && x->n_cols * 8 <= x->n_cells &&
+            need <= (size_t(1) << 31)) {
+          if (x->col_terms_bytes < need) {   // grows to the largest launch seen; a failed allocation leaves the plain path
+            if (x->col_terms) cudaFree(x->col_terms);
+            x->col_terms = nullptr; x->col_terms_bytes = 0;
+            const size_t want = (size_t)std::min<int64_t>(tfg::kMaxLaunchSteps, std::max<int32_t>(nt, n_steps)) * (size_t)x->n_cols *
+                                tfg::kCtCount * sizeof(double);
+            if (cudaMalloc(&x->col_terms, want) == cudaSuccess) x->col_terms_bytes = want;
+            else (void)cudaGetLastError();
+          }
+          if (x->col_terms_bytes >= need) {
+            e = tfg::launch_column_terms_fast(static_cast<const double*>(f), x->col_terms, nt, x->n_cols, p.k, s);
+            p.col_terms = x->col_terms;
+            ++x->col_term_launches;
+          }
+        }
+        if (e == cudaSuccess) e = tfg::launch_run_fast(p, rec, agg, vol, s);
+      }
     }
   }
   if (e != cudaSuccess) return fail("tfg_run: kernel launch", e);

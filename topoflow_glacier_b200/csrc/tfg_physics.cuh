@@ -476,15 +476,97 @@ __device__ __forceinline__ void lean_state(const Consts<double>& k, Cell& s, Cel
   o.Q_sum = Q_sum; o.P_rain = P_rain; o.P_snow = P_snow;
 }
 
+// ---- column terms -----------------------------------------------------------------------------------------------------
+// With a forcing map bound (tfg_bind_forcing_map: how every catchment run is configured -- one met series per
+// catchment, many cells) the part of update() that reads nothing but the forcings is the same for every cell of a
+// column: vapour pressures, relative humidity, dew point (:423-425, :784-893), precipitable water (:919-920), air
+// emissivity and incoming longwave (:1167-1234), the snowfall wet bulb (:1507-1520).  `column_terms_eval` evaluates it
+// ONCE PER COLUMN AND TIMESTEP (tfg::column_terms_kernel) with exactly the operations of the per-cell fast step, and the
+// melt kernel reads the results: one 128-byte line per column and timestep, which also carries the raw forcings, so
+// the per-cell forcing block is not read at all.  What stays per cell: pressure at the cell's elevation, the log law,
+// the bulk exchange, albedo, clear-sky shortwave on the cell's slope, the melt / cold-content / water-equivalent updates.
+enum { kCtP, kCtTair, kCtUz, kCtRTK, kCtEair, kCtRH, kCtTdew, kCtSane,        // read ahead (next step) by the kernel
+       kCtWp, kCtEsDew, kCtLWin, kCtTwb, kCtEmAir, kCtEsatAir, kCtPair, kCtQ,  // read at their point of use
+       kCtCount };
+static_assert(kCtCount == 16, "one 128-byte line per column and timestep");
+struct NoColumnTerms { static constexpr bool on = false; };
+struct ColumnTerms {
+  static constexpr bool on = true;
+  double rTK, e_air, RH, T_dew;   // in registers (prefetched with the forcings)
+  const double* line;             // this step's line: the remaining terms are loaded where they are consumed
+  __device__ __forceinline__ double get(int i) const { return __ldg(line + i); }
+};
+
+// the forcing-only terms of one column and timestep; `sane` as in the melt kernel's fast-path test (otherwise the
+// kernel takes the strict step from the raw forcings and none of the terms is read)
+template <class P>
+__device__ __forceinline__ void column_terms_eval(const Consts<double>& k, double Pp, double T_air_, double P_air_, double q_,
+                                                  double uz, bool sane, double* out) {
+  using R = Num<P>;
+  static_assert(P::lean, "column terms exist for the fast float64 mode only");
+  double o[kCtCount];
+#pragma unroll
+  for (int i = 0; i < kCtCount; ++i) o[i] = 0.0;
+  o[kCtP] = Pp; o[kCtTair] = T_air_; o[kCtUz] = uz; o[kCtPair] = P_air_; o[kCtQ] = q_;
+  if (sane) {
+    const R T_air(T_air_), P_air(P_air_), q(q_);
+    const R T_K = T_air + LIT(kelvin, 273.15);
+    const double den3[3] = {T_K.v, fmadd(R(k.one_m_eps), q, R(k.eps)).v, (T_air + LIT(mag_b, 237.3)).v};
+    double rc3[3];
+    fm::rcp3_n<3>(den3, rc3);
+    const R rTK(rc3[0]);
+    const R e = (q * P_air) * R(rc3[1]);
+    const R e_air = e * LIT(c001, 0.01);
+    const double ex1[1] = {(-((LIT(mag_a, 17.3) * T_air) * R(rc3[2]))).v};
+    const double lx1[1] = {(e_air * LIT(inv_dew_a, 0.1636098885816659)).v};
+    double ey1[1], ly1[1];
+    fm::exp_tab_n<1>(ex1, ey1);
+    fm::log_tab_n<1>(lx1, ly1);
+    const R en(ey1[0]), log_term(ly1[0]);
+    const R RH = (e_air * en) * LIT(inv_esat0, 0.1636661211129296);
+    const R T_dew = (LIT(dew_c, 257.14) * log_term) * R(fm::rcp3((LIT(dew_b, 18.678) - log_term).v));
+    const double den1[1] = {(T_dew + LIT(mag_b, 237.3)).v};
+    double rc1[1];
+    fm::rcp3_n<1>(den1, rc1);
+    const double ex2[2] = {(LIT(wp_b, 0.0614) * T_dew).v, ((LIT(mag_a, 17.3) * T_dew) * R(rc1[0])).v};
+    double ey2[2];
+    fm::exp_tab_n<2>(ex2, ey2);
+    const R W_p = LIT(wp_a, 1.12) * R(ey2[0]);
+    const R es_dew = LIT(esat10, 6.11) * R(ey2[1]);
+    const R x = (e_air * LIT(c01, 0.1)) * rTK;
+    const R em_air = fmadd(R(k.emis_a) * R(fm::root7(x.v)), R(k.emis_b), R(k.canopy));
+    const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);
+    R T_wb;
+    bool stull_fast;
+    if constexpr (TFG_WETBULB_TABLE) stull_fast = (RH >= 0.046875) && (RH <= 2.0);
+    else stull_fast = (RH >= 0.0) && (RH <= 2.0);
+    if (stull_fast) {
+      if constexpr (TFG_WETBULB_TABLE) T_wb = R(fm::stull_wet_bulb_tab(T_air.v, RH.v));
+      else T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));
+    } else {
+      T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
+               natan(RH - LIT(st_c, 1.676331))) +
+              ((LIT(st_d, 0.00391838) * npow15(RH)) * natan(LIT(st_e, 0.023101) * RH))) -
+             LIT(st_f, 4.86035);
+    }
+    o[kCtRTK] = rTK.v; o[kCtEair] = e_air.v; o[kCtRH] = RH.v; o[kCtTdew] = T_dew.v; o[kCtSane] = 1.0;
+    o[kCtWp] = W_p.v; o[kCtEsDew] = es_dew.v; o[kCtLWin] = LW_in.v; o[kCtTwb] = T_wb.v; o[kCtEmAir] = em_air.v;
+    o[kCtEsatAir] = (LIT(esat10, 6.11) / en).v;
+  }
+#pragma unroll
+  for (int i = 0; i < kCtCount; i += 2) *reinterpret_cast<double2*>(out + i) = make_double2(o[i], o[i + 1]);
+}
+
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
 // `mid_step()` is called once the pressure / humidity / wind forcings are dead (after the turbulent fluxes): the
 // kernel issues the next step's forcing loads there, so that they do not hold registers through the met block.
-template <class P, bool VOL, class Cell, class WindowFn, class MidFn>
+template <class P, bool VOL, class Cell, class WindowFn, class MidFn, class Pre = NoColumnTerms>
 __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, const TimeRow<typename P::raw>& tr,
                                           Cell& s, Num<P> LC, CellState<typename P::raw>& st,
                                           Num<P> Pp, Num<P> T_air, Num<P> P_air, Num<P> q, Num<P> uz,
-                                          WindowFn&& window_sum, MidFn&& mid_step, StepOut<typename P::raw>& o) {
+                                          WindowFn&& window_sum, MidFn&& mid_step, StepOut<typename P::raw>& o,
+                                          const Pre& pre = Pre()) {
   using R = Num<P>;
 #if TFG_SPLIT_STEP   // experiment: the fast float64 step through lean_forcing / lean_state (measured 3 % slower, see below)
   if constexpr (P::lean) {
@@ -520,7 +602,49 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   R p0, e_sat_air, e_air, RH, T_dew, T_surf, e_sat_surf, dT, Ri, Dn, Dh, Qh, W_p, e_surf, Qe, rTK;
   R n_early, tot_early, alb_exp;   // lean + TFG_ALBEDO_EARLY: days since snowfall, window sum, exp(-n r)
   double root7_pre = 0.0;   // x**(1/7) of update_em_air, evaluated early beside two exponentials (lean, TFG_FUSE_ROOT7)
-  if constexpr (P::lean) {
+  if constexpr (P::lean && Pre::on) {
+    // Column terms bound (see column_terms_eval): only what depends on the cell is left of the met block
+    static_assert(TFG_ALBEDO_EARLY && TFG_FOLD_CONSTS, "the column-term step is written for the default fast step");
+    rTK = R(pre.rTK); e_air = R(pre.e_air); RH = R(pre.RH); T_dew = R(pre.T_dew);
+    const double lx1[1] = {nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)).v};
+    double ly1[1];
+    fm::log_tab_n<1>(lx1, ly1);
+    const R L(ly1[0]);
+    const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
+    T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);                                         // :906-911
+    dT = T_air - T_surf;
+    const R top = R(k.gz) * dT;                                                              // :640-644
+    R bot = (uz * uz) * T_K;
+    bot = sel(bot == 0.0, LIT(c001, 0.01), bot);
+    const bool stable = top > 0.0;
+    const R num = sel(stable, bot, fnmadd(R(10.0), top, bot));
+    const R den = sel(stable, fmadd(R(10.0), top, bot), bot);
+    const R uk2 = uz * R(k.kappa2);
+    const R LL = L * L;
+    const double den1[1] = {(LL * den).v};
+    double rc1[1];
+    fm::rcp3_n<1>(den1, rc1);
+    Dh = (uk2 * num) * R(rc1[0]);
+    // albedo ageing (:1023-1048) beside the pressure exponential (:551-556)
+    const R r = sel(T_air > 0.0, LIT(alb_r1, 0.12), LIT(alb_r0, 0.05));
+    const R ring_new = xmul(xmul(P_snow, dt), R(k.ws_ratio));  // :1031-1033
+    tot_early = R(window_sum(ring_new.v));                     // :1027-1037
+    n_early = sel(tot_early < LIT(snow_thr, 0.03), R(st.n_days) + R(k.days_per_dt), R(0.0));
+    const double ex2[2] = {(-(R(s.get(kSaElevR)) * rTK)).v, ((-n_early) * r).v};
+    double ey2[2];
+    fm::exp_tab_n<2>(ex2, ey2);
+    alb_exp = R(ey2[1]);
+    const R inv_p0 = R(ey2[0]) * R(k.inv_p0c);
+    W_p = R(pre.get(kCtWp));
+    // e_sat(T_surf): T_surf is the dew point, or 0 degC over a melting surface, where exp(17.3 * 0 / 237.3) = 1 exactly
+    e_sat_surf = sel(cover && (T_dew > 0.0), LIT(esat10, 6.11) * R(1.0), R(pre.get(kCtEsDew)));
+    Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
+    e_surf = RH * e_sat_surf;                                                                // :853
+    Qe = (Dh * fnmadd(RH, e_sat_surf, e_air)) * (R(ey2[0]) * R(k.cq0));                      // :931-934
+    // only read when a caller records them (dead code otherwise)
+    p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
+    e_sat_air = R(pre.get(kCtEsatAir));
+  } else if constexpr (P::lean) {
     // Same quantities with 7 instead of 12 divisions: 1/T_K is shared, 1/p0 and RH come from exp(-x) instead of
     // dividing by exp(x), and the aerodynamic block (:640-733) collapses into one quotient:
     //   stable   (top > 0): Dh = Dn / (1 + 10 top/bot) = uz k^2 bot          / (L^2 (bot + 10 top))
@@ -666,7 +790,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   const R Qn_SW = K_cs * (R(1.0) - albedo);
   // ---- update_em_air :1167-1192
   R em_air;
-  if (P::lean || !k.satterlund) {
+  if constexpr (Pre::on) {
+    em_air = R(pre.get(kCtEmAir));   // recording only
+  } else if (P::lean || !k.satterlund) {
     R x;
     if constexpr (P::lean) x = (e_air * LIT(c01, 0.1)) * rTK; else x = divk(e_air, 10.0) / T_K;
     R term1;
@@ -679,7 +805,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   }
   // ---- update_net_longwave_radiation :1231-1248
   const R T_surf_K = T_surf + LIT(kelvin, 273.15);
-  const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);
+  R LW_in;
+  if constexpr (Pre::on) LW_in = R(pre.get(kCtLWin)); else LW_in = (em_air * R(k.sigma)) * npow4(T_K);
   R LW_out = R(k.es_sigma) * npow4(T_surf_K);
   LW_out = fmadd(R(k.one_m_es), LW_in, LW_out);
   const R Qn_LW = LW_in - LW_out;
@@ -712,7 +839,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     bool stull_fast = false;
     if constexpr (P::lean && TFG_WETBULB_TABLE) stull_fast = (RH >= 0.046875) && (RH <= 2.0);   // table bins 1..32
     else if constexpr (P::lean || P::f32) stull_fast = (RH >= 0.0) && (RH <= 2.0);
-    if (stull_fast) {
+    if constexpr (Pre::on) {
+      T_wb = R(pre.get(kCtTwb));
+    } else if (stull_fast) {
       if constexpr (P::f32) T_wb = R(fm::stull_wet_bulb32(T_air.v, RH.v));
       else if constexpr (TFG_WETBULB_TABLE) T_wb = R(fm::stull_wet_bulb_tab(T_air.v, RH.v));
       else T_wb = R(fm::stull_wet_bulb(T_air.v, RH.v));

@@ -71,10 +71,27 @@ struct RunParams {
   int32_t n_basin, agg_exact;
   double agg_up[TFG_N_AGG];  // 2^(40 - E_q)
   long long* agg_bad;   // exact mode: count of contributions left out (non-finite or >= 2^E_q)
-  Consts<raw> k;
+  // 16-byte aligned: ptxas pairs neighbouring constants into 128-bit uniform loads; with the block 8 bytes off the fast
+  // kernel loses 2 % (measured: profiles/r2_experiments.md).  New members go behind it.
+  alignas(16) Consts<raw> k;
+  const raw* col_terms;        // optional [n_steps][n_cols][kCtCount] (fast float64 mode, forcing map bound): the column
+                               // terms of this launch (column_terms_kernel); the kernel then does not read `forcing`
 };
 
 template <class raw> __device__ __forceinline__ raw ld_stream(const raw* p) { return __ldcs(p); }
+
+// The fast step is written for physically meaningful forcings (no guards, no NaN rules); anything else -- missing data,
+// absurd values -- takes the strict step.  Integer tests on the high words: one ALU instruction per bound.
+template <class raw>
+__device__ __forceinline__ bool forcings_sane(raw f0, raw f1, raw f2, raw f3, raw f4) {
+  auto in_range = [](raw v, double lo, double hi) {
+    const unsigned h = (unsigned)__double2hiint(v), l = (unsigned)__double2hiint(lo), u = (unsigned)__double2hiint(hi);
+    return (h - l) < (u - l);
+  };
+  return ((unsigned)__double2hiint(f0) < (unsigned)__double2hiint(10.0)) &&
+         (((unsigned)__double2hiint(f1) & 0x7fffffffu) < (unsigned)__double2hiint(90.0)) &&
+         in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) && (in_range(f4, 1e-100, 200.0) || f4 == 0.0);
+}
 
 // One element global -> shared without a register in between (LDGSTS): the next step's forcings are in flight for a
 // whole timestep, and as register prefetches they would pin ten registers for that long.
@@ -161,7 +178,7 @@ __device__ __forceinline__ void agg_add_exact(long long* acc, double v, double u
   if (b) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + 1, (unsigned long long)b);
 }
 
-template <class P, bool REC, bool AGG, bool VOL, bool TMA = false>
+template <class P, bool REC, bool AGG, bool VOL, bool TMA = false, bool PRE = false>
 __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f32 ? TFG_MIN_BLOCKS_F32 : TFG_MIN_BLOCKS)) run_kernel(const __grid_constant__ RunParams<typename P::raw> p) {
   using raw = typename P::raw;
   using R = Num<P>;
@@ -238,9 +255,20 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
 
   // forcing block [step][var][column]: column = cell, or the cell's entry of the forcing map
+  static_assert(!PRE || (P::lean && !TMA), "column terms: fast float64 mode, register prefetch");
   const int64_t FN = p.n_cols;
-  const raw* f = p.forcing + (p.forcing_col ? (int64_t)__ldg(p.forcing_col + c) : c);
-  raw f0, f1, f2, f3, f4;
+  // PRE: one line of kCtCount values per column and timestep instead of five forcing rows
+  const raw* f = PRE ? p.col_terms + (int64_t)__ldg(p.forcing_col + c) * kCtCount
+                     : p.forcing + (p.forcing_col ? (int64_t)__ldg(p.forcing_col + c) : c);
+  raw f0, f1, f2, f3, f4;        // PRE: P, T_air, 1/T_K, e_air, uz
+  raw e0 = 0, e1 = 0, e2 = 0;    // PRE: RH, T_dew, "forcings sane"
+  auto load_line = [](const raw* l, raw& a0, raw& a1, raw& a2, raw& a3, raw& a4, raw& b0, raw& b1, raw& b2) {
+    if constexpr (PRE) {
+      const double2 q0 = __ldg(reinterpret_cast<const double2*>(l + kCtP)), q1 = __ldg(reinterpret_cast<const double2*>(l + kCtUz)),
+                    q2 = __ldg(reinterpret_cast<const double2*>(l + kCtEair)), q3 = __ldg(reinterpret_cast<const double2*>(l + kCtTdew));
+      a0 = q0.x; a1 = q0.y; a4 = q1.x; a2 = q1.y; a3 = q2.x; b0 = q2.y; b1 = q3.x; b2 = q3.y;
+    }
+  };
   __shared__ alignas(128) raw sm_force[TMA ? kStages : 1][TFG_N_FORCING][TMA ? kBlock : 1];
   __shared__ uint64_t bar_full[kStages], bar_empty[kStages];
   const raw* fblock = p.forcing + (int64_t)blockIdx.x * kBlock;  // first cell of this block, step 0, variable 0
@@ -272,6 +300,8 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       for (int i = 0; i < kStages && i < p.n_steps; ++i) issue_stage(i);
   } else if constexpr (kCp) {
     stage_forcing(0);
+  } else if constexpr (PRE) {
+    load_line(f, f0, f1, f2, f3, f4, e0, e1, e2);
   } else {
     f0 = ld_stream(f); f1 = ld_stream(f + FN); f2 = ld_stream(f + 2 * FN); f3 = ld_stream(f + 3 * FN);
     f4 = ld_stream(f + 4 * FN);
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
   StepOut<raw> o;
   for (int t = 0; t < p.n_steps; ++t) {
-    raw g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0;
+    raw g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0;
     if constexpr (TMA) {
       const int sg = t % kStages;
       mbar_wait(&bar_full[sg], (unsigned)((t / kStages) & 1));
@@ -387,7 +417,10 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     auto prefetch = [&]() {  // next step's forcings, issued mid-step (see cell_step)
       if constexpr (!TMA && !kCp) {
         g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
-        if (t + 1 < p.n_steps) {
+        if constexpr (PRE) {
+          g5 = e0; g6 = e1; g7 = e2;
+          if (t + 1 < p.n_steps) load_line(f + (int64_t)(t + 1) * (kCtCount * FN), g0, g1, g2, g3, g4, g5, g6, g7);
+        } else if (t + 1 < p.n_steps) {
           const raw* fn = f + (int64_t)(t + 1) * (TFG_N_FORCING * FN);
           g0 = ld_stream(fn); g1 = ld_stream(fn + FN); g2 = ld_stream(fn + 2 * FN); g3 = ld_stream(fn + 3 * FN);
           g4 = ld_stream(fn + 4 * FN);
@@ -397,23 +430,27 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     if constexpr (P::lean) {
       // The lean math cores assume physically sane arguments.  Bit tests on the high words (no FP64 pipe):
       // P in [0, 10) m/h, |T_air| < 90 degC, P_air in [1e3, 2e5) Pa, q in [1e-7, 0.2), uz = 0 or in [1e-100, 200)
-      auto in_range = [](raw v, double lo, double hi) {
-        const unsigned h = (unsigned)__double2hiint(v), l = (unsigned)__double2hiint(lo), u = (unsigned)__double2hiint(hi);
-        return (h - l) < (u - l);
-      };
-      const bool sane = ((unsigned)__double2hiint(f0) < (unsigned)__double2hiint(10.0)) &&
-                        (((unsigned)__double2hiint(f1) & 0x7fffffffu) < (unsigned)__double2hiint(90.0)) &&
-                        in_range(f2, 1e3, 2e5) && in_range(f3, 1e-7, 0.2) &&
-                        (in_range(f4, 1e-100, 200.0) || f4 == 0.0) && statics_sane;
+      bool sane;
+      if constexpr (PRE) sane = (__double2hiint(e2) != 0) && statics_sane;   // the column's forcings were tested once, by column_terms_kernel
+      else sane = forcings_sane(f0, f1, f2, f3, f4) && statics_sane;
       // (SATTERLUND = True, a rarely used configuration switch, also takes the strict step: the lean one is
       // written for the default Magnus / Brutsaert formulas only, which keeps it free of configuration branches)
       if (__all_sync(0xffffffffu, sane && state_ok) && !p.k.satterlund) {
-        cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
+        if constexpr (PRE) {
+          const ColumnTerms pre{f2, f3, e0, e1, f + (int64_t)t * (kCtCount * FN)};
+          cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(0.0), R(0.0), R(f4), window, prefetch, o, pre);
+        } else {
+          cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
+        }
       } else {
         // Same step in the strict arithmetic (libdevice, IEEE division, NumPy's NaN rules): whatever the input
         // -- missing data, absurd values -- the cell behaves like the reference, NaN poisoning included.
         using S = Num<StrictF64>;
         const S LCs = ((S(gmt_prev) * 15.0) - S(lon.v)) / 15.0;
+        if constexpr (PRE) {  // the line carries the raw pressure and humidity for this case
+          const raw* line = f + (int64_t)t * (kCtCount * FN);
+          f2 = __ldg(line + kCtPair); f3 = __ldg(line + kCtQ);
+        }
         cell_step<StrictF64, VOL>(p.k, row, s, LCs, st, S(f0), S(f1), S(f2), S(f3), S(f4), window, prefetch, o);
         state_ok = finite(st.h_snow) && finite(st.h_swe) && finite(st.h_ice) && finite(st.h_iwe) &&
                    finite(st.eccs) && finite(st.ecci) && finite(st.albedo) && finite(st.n_days);
@@ -488,6 +525,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       }
     }
     if constexpr (!TMA && !kCp) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
+    if constexpr (PRE) { e0 = g5; e1 = g6; e2 = g7; }
     r_old = r_next;
     slot = slot_next;
     if constexpr (kWalk) ring_cur = ring_next;
@@ -514,6 +552,32 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
 }
 
 // host-side dispatch over the compile-time switches; defined once per arithmetic mode (one TU each)
+// Column terms of one launch: thread = (timestep, column) of the forcing block [n_steps][5][n_cols]; writes one line of
+// kCtCount doubles (see tfg_physics.cuh).  Compiled in the fast translation unit, with the melt kernel's own device
+// functions, so the values equal what the per-cell step computes (tests: mapped forcing == replicated forcing, bit for bit).
+template <class P>
+__global__ void __launch_bounds__(256) column_terms_kernel(const double* __restrict__ forcing, double* __restrict__ out,
+                                                           int32_t n_steps, int64_t n_cols, const Consts<double> k) {
+  for (int i = threadIdx.x; i < fm::kTabDoubles; i += blockDim.x)
+    fm::tfg_tabs[i] = (i < 64) ? fm::kExpTab[i] : fm::kLogTab[(i - 64) >> 1][(i - 64) & 1];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_steps * n_cols) return;
+  const int64_t t = idx / n_cols, col = idx - t * n_cols;
+  const double* f = forcing + t * (TFG_N_FORCING * n_cols) + col;
+  const double f0 = f[0], f1 = f[n_cols], f2 = f[2 * n_cols], f3 = f[3 * n_cols], f4 = f[4 * n_cols];
+  column_terms_eval<P>(k, f0, f1, f2, f3, f4, forcings_sane(f0, f1, f2, f3, f4), out + idx * kCtCount);
+}
+
+template <class P>
+cudaError_t launch_column_terms(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
+                                cudaStream_t stream) {
+  const int64_t total = (int64_t)n_steps * n_cols;
+  column_terms_kernel<P><<<(unsigned)((total + 255) / 256), 256, fm::kTabDoubles * sizeof(double), stream>>>(forcing, out, n_steps,
+                                                                                                           n_cols, k);
+  return cudaGetLastError();
+}
+
 template <class P>
 cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, bool vol, cudaStream_t stream) {
   const unsigned grid = (unsigned)((p.n_cells + kBlock - 1) / kBlock);
@@ -522,6 +586,16 @@ cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, 
                    ((reinterpret_cast<uintptr_t>(p.forcing) & 15) == 0) &&
                    ((p.n_cells * sizeof(typename P::raw)) % 16 == 0);
   const size_t dyn = P::lean ? fm::kTabDoubles * sizeof(double) : 0;
+  if constexpr (P::lean) {
+    if (p.col_terms != nullptr) {  // column terms bound (forcing map): the kernel reads them instead of the forcing block
+      if (rec) run_kernel<P, true, true, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
+      else if (agg && vol) run_kernel<P, false, true, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
+      else if (agg) run_kernel<P, false, true, false, false, true><<<grid, kBlock, dyn, stream>>>(p);
+      else if (vol) run_kernel<P, false, false, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
+      else run_kernel<P, false, false, false, false, true><<<grid, kBlock, dyn, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
   if (rec) run_kernel<P, true, true, true><<<grid, kBlock, dyn, stream>>>(p);
   else if (tma) {
     if (agg && vol) run_kernel<P, false, true, true, true><<<grid, kBlock, dyn, stream>>>(p);
@@ -539,5 +613,7 @@ cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, 
 cudaError_t launch_run_strict(const RunParams<double>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
 cudaError_t launch_run_fast(const RunParams<double>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
 cudaError_t launch_run_f32(const RunParams<float>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
+cudaError_t launch_column_terms_fast(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
+                                     cudaStream_t stream);
 
 }  // namespace tfg

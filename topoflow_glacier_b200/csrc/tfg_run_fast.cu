@@ -24,10 +24,14 @@ cudaError_t launch_run_fast(const RunParams<double>& p, bool rec, bool agg, bool
 #else
   // Recording launches, one-step launches (exact window re-sum: the literal update()), TMA staging and SATTERLUND
   // configurations stay with the single-stream kernel; all routes evaluate the same device functions.
-  const bool fused = !p.exact_ring && !p.use_tma;
+  const bool fused = !p.exact_ring && !p.use_tma && !p.col_terms;
   if (TFG_WS && fused && !rec && !p.k.satterlund && p.n_steps >= 2) return launch_run_ws(p, agg, vol, stream);
   if (TFG_PIPELINE && fused) return launch_run_pipe(p, rec, agg, vol, stream);
   return launch_run<FastF64>(p, rec, agg, vol, stream);
 #endif
+}
+cudaError_t launch_column_terms_fast(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
+                                     cudaStream_t stream) {
+  return launch_column_terms<FastF64>(forcing, out, n_steps, n_cols, k, stream);
 }
 }  // namespace tfg

@@ -60,7 +60,8 @@ class MeltEngine:
                  zones: Sequence = ("America/Los_Angeles",), tz_idx: Optional[np.ndarray] = None,
                  basin_id: Optional[np.ndarray] = None, n_basin: int = 0, mode: str = "f64", device: int = 0,
                  horizon_steps: int = 24 * 366, diag_integrals: bool = True, device_statics: Optional[dict] = None,
-                 tma_staging: Optional[bool] = None, forcing_index=None, n_forcing_cols: Optional[int] = None):
+                 tma_staging: Optional[bool] = None, forcing_index=None, n_forcing_cols: Optional[int] = None,
+                 column_terms: Optional[bool] = None):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.mode = _lib.MODE_NAMES[mode] if isinstance(mode, str) else int(mode)
@@ -87,6 +88,10 @@ class MeltEngine:
                 tma_staging = os.environ.get("TFG_TMA_STAGING", "0") == "1"
             self.tma_staging = bool(tma_staging)
             _lib.check(self.lib.tfg_set_option(ctx, _lib.OPT_TMA_STAGING, int(self.tma_staging)), "tfg_set_option")
+            if column_terms is None:  # TFG_OPT_COLUMN_TERMS: forcing-only terms once per forcing column (default on)
+                column_terms = os.environ.get("TFG_COLUMN_TERMS", "1") != "0"
+            self.column_terms = bool(column_terms)
+            _lib.check(self.lib.tfg_set_option(ctx, _lib.OPT_COLUMN_TERMS, int(self.column_terms)), "tfg_set_option")
             self._set_constants()
             if device_statics is not None:  # synthetic grids: tables already on the device
                 self.N = int(next(iter(device_statics.values())).numel())
@@ -361,6 +366,11 @@ class MeltEngine:
         v = C.c_double()
         _lib.check(self.lib.tfg_measure_fp64_peak(self.ctx, C.byref(v), self.stream_ptr), "tfg_measure_fp64_peak")
         return float(v.value)
+
+    @property
+    def column_term_launches(self) -> int:
+        """Launches that evaluated the forcing-only terms once per forcing column (``TFG_OPT_COLUMN_TERMS``)."""
+        return int(self.lib.tfg_column_term_launches(self.ctx))
 
     def close(self):
         if getattr(self, "ctx", None):
