@@ -808,3 +808,35 @@ def test_column_terms_pass_is_bit_identical_and_taken(cuda_device):
         assert torch.equal(out[True][i].view(torch.int64), out[False][i].view(torch.int64))
     assert torch.equal(out[True][3], out[False][3])                # exact basin sums and the left-out counter
     assert torch.isnan(out[True][1]).any()                         # the missing value did poison its cells
+
+
+def test_column_terms_on_the_per_step_path(cuda_device):
+    """The literal update() (one-step launches, exact window re-sum) with the column-term pass in front: same state as
+    without it, and as the fused launch, bit for bit (large enough for the pass to be taken: >= 65536 cell-steps)."""
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    N, M, T = 66000, 16, 5
+    statics, _ = bench.synthetic_host_sample(N, 1, seed=21)
+    _, fcols = bench.synthetic_host_sample(M, T, seed=22)
+    col = (np.arange(N) % M).astype(np.int32)
+    kw = dict(zones=[-8.0], mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M)
+    f = torch.as_tensor(np.ascontiguousarray(fcols)).to(cuda_device, torch.float64).contiguous()
+    states = []
+    for on, fused in ((True, False), (False, False), (True, True)):
+        e = MeltEngine(statics, default_constants(), "2013020100", column_terms=on, **kw)
+        if fused:
+            e.run(f)
+        else:
+            for t in range(T):
+                e.inputs[:5].copy_(f[t])
+                e.step()
+        torch.cuda.synchronize()
+        assert (e.column_term_launches > 0) == on
+        states.append((e.state.clone(), e.ring.clone()))
+        e.close()
+    for s, r in states[1:]:
+        assert torch.equal(states[0][0], s) and torch.equal(states[0][1], r)

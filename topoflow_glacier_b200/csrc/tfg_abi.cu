@@ -433,8 +433,9 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
         // timestep (column_terms_kernel) and the melt kernel reads one line per step instead of redoing it per cell.
         // Same device functions either way: results do not depend on this switch (test_column_terms_*).
         const size_t need = (size_t)nt * (size_t)x->n_cols * tfg::kCtCount * sizeof(double);
+        // (not for launches so small that a second kernel launch costs more than it saves: per-step BMI updates of a few cells)
         if (x->column_terms && x->forcing_col && !x->use_tma && !x->c.satterlund && x->n_cols * 8 <= x->n_cells &&
-            need <= (size_t(1) << 31)) {
+            (int64_t)nt * x->n_cells >= 65536 && need <= (size_t(1) << 31)) {
           if (x->col_terms_bytes < need) {   // grows to the largest launch seen; a failed allocation leaves the plain path
             if (x->col_terms) cudaFree(x->col_terms);
             x->col_terms = nullptr; x->col_terms_bytes = 0;

@@ -26,6 +26,9 @@ namespace tfg {
 #ifndef TFG_CPASYNC  // 1: next-step forcings staged in shared memory by cp.async instead of register prefetches (measured slower)
 #define TFG_CPASYNC 0
 #endif
+#ifndef TFG_CT_REGPF   // column-term kernel: 1 = next step's line prefetched into registers mid-step; 0 = one L1 prefetch of the line
+#define TFG_CT_REGPF 0 // mid-step and 128-bit loads at the top of the step (the line is shared by the warp: 38.8 vs 38.3 G)
+#endif
 #ifndef TFG_WALK_LEAN  // 1: the fast float64 kernel carries the window-slot pointer (as the float32 kernel does) instead of re-deriving it
 #define TFG_WALK_LEAN 0   // measured slower (30.6 vs 31.2 G): two more live registers at the 96-register limit
 #endif
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
       f3 = sm_next[t & 1][3][threadIdx.x]; f4 = sm_next[t & 1][4][threadIdx.x];
       if (t + 1 < p.n_steps) stage_forcing(t + 1);
     }
+    if constexpr (PRE && !TFG_CT_REGPF) { if (t > 0) load_line(f + (int64_t)t * (kCtCount * FN), f0, f1, f2, f3, f4, e0, e1, e2); }
     const TimeRow<raw>& row = p.rows[t];
     if (!TFG_ZONE_ONCE || p.gmt_varies) {  // a DST switch falls into this launch (twice a year): follow the offset step by step
       const raw gmt = p.gmt[t * p.n_tz + tz];
@@ -417,7 +421,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
     auto prefetch = [&]() {  // next step's forcings, issued mid-step (see cell_step)
       if constexpr (!TMA && !kCp) {
         g0 = f0; g1 = f1; g2 = f2; g3 = f3; g4 = f4;
-        if constexpr (PRE) {
+        if constexpr (PRE && !TFG_CT_REGPF) {
+          if (t + 1 < p.n_steps) asm volatile("prefetch.global.L1 [%0];" ::"l"(f + (int64_t)(t + 1) * (kCtCount * FN)));
+        } else if constexpr (PRE) {
           g5 = e0; g6 = e1; g7 = e2;
           if (t + 1 < p.n_steps) load_line(f + (int64_t)(t + 1) * (kCtCount * FN), g0, g1, g2, g3, g4, g5, g6, g7);
         } else if (t + 1 < p.n_steps) {
@@ -524,8 +530,11 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         }
       }
     }
-    if constexpr (!TMA && !kCp) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
-    if constexpr (PRE) { e0 = g5; e1 = g6; e2 = g7; }
+    if constexpr (PRE && !TFG_CT_REGPF) {
+    } else {
+      if constexpr (!TMA && !kCp) { f0 = g0; f1 = g1; f2 = g2; f3 = g3; f4 = g4; }
+      if constexpr (PRE) { e0 = g5; e1 = g6; e2 = g7; }
+    }
     r_old = r_next;
     slot = slot_next;
     if constexpr (kWalk) ring_cur = ring_next;
