@@ -65,13 +65,19 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark = index, [], None, 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi needs a few hundred ms to come up (longer on an 8-GPU box): wait for its first line so that
+            # a timed region of a few hundred ms is sampled from its first millisecond; only later rows are counted
+            t0 = time.monotonic()
+            while not self.rows and time.monotonic() - t0 < 8.0 and self.proc.poll() is None:
+                time.sleep(0.02)
+            self.mark = len(self.rows)
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -84,7 +90,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in (self.rows[self.mark:] or self.rows[-1:]):   # the rows of the timed region (else the one just before it)
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -657,10 +663,10 @@ def run_gpu_arm(args):
         for m in ("f64", "f32"):
             if m == mode:
                 continue
-            e2, el2, _, z2, r2, tot2, _, a2 = make_engine(m, args.cells, False, 4096, Tc, (args.warmup + 6) * Tc + 64)
+            e2, el2, _, z2, r2, tot2, _, a2 = make_engine(m, args.cells, False, 4096, Tc, (args.warmup + 30) * Tc + 64)
             f2 = torch.empty(Tc, 5, e2.N, dtype=e2.dtype, device=dev)
             e2.synth_forcing(f2, 0, Tc, el2.to(e2.dtype), seed=20121001 + rank)
-            nrep = 2 if m == "f64" else max(3, args.steps // 2)
+            nrep = 2 if m == "f64" else max(3, args.steps // 2, 20)   # f32: >= 0.7 s of timed region for the clock sampler
             for _ in range(2):
                 e2.run(f2, Tc, basin_agg=z2())
             (kms, dms), clk = clocked(lambda: time_launches(e2, f2, Tc, z2, r2, nrep, 1, dev))
@@ -674,13 +680,14 @@ def run_gpu_arm(args):
         # BASELINE configs[4]: ONE 100 M-cell grid sharded over the GPUs (strong scaling) through ShardedMeltEngine;
         # timesteps per launch grow with the GPU count (the shard shrinks): 16 on one GPU ... 128 on eight
         Tr = min(128, 16 * world)
-        e3, el3, _, z3, r3, tot3, _, a3 = make_engine(mode, REGIONAL_CELLS, True, 100, Tr, (args.warmup + args.steps + 3) * Tr + 64)
+        e3, el3, _, z3, r3, tot3, _, a3 = make_engine(mode, REGIONAL_CELLS, True, 100, Tr, (args.warmup + args.steps + 64) * Tr + 64)
         f3 = torch.empty(Tr, 5, e3.N, dtype=e3.dtype, device=dev)
         e3.synth_forcing(f3, 0, Tr, el3.to(e3.dtype), seed=20121001 + rank)
         for _ in range(3):
             e3.run(f3, Tr, basin_agg=z3())
             r3()
-        nrep = max(3, args.steps // 2)
+        k_est, _ = time_launches(e3, f3, Tr, z3, r3, 1, world, dev)
+        nrep = max(3, args.steps // 2, int(-(-800.0 // k_est)))   # >= 0.8 s of timed region: the clock sampler ticks every 100 ms
         (kms, dms), clk = clocked(lambda: time_launches(e3, f3, Tr, z3, r3, nrep, world, dev))
         strong = {"value": tot3 * Tr * nrep / (dms * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": world,
                   "cells_total": tot3, "cells_per_gpu": e3.N, "timesteps_per_step": Tr, "steps": nrep,
