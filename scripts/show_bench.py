@@ -2,7 +2,11 @@
 import json
 import sys
 
-d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+txt = open(sys.argv[1]).read().strip()
+try:
+    d = json.loads(txt)                      # pretty-printed copy under profiles/
+except json.JSONDecodeError:
+    d = json.loads(txt.splitlines()[-1])     # the one-line original
 if d.get("impl") == "reference":
     print("reference", d.get("value"), d.get("cpu_baseline"))
     sys.exit(0)
