@@ -463,3 +463,39 @@ def test_window_sum_recovers_from_missing_precipitation(mode, chunk, cuda_device
     assert np.array_equal(got["n"][:, 2:], want["n"][:, 2:])                      # untouched cells: exact
     np.testing.assert_array_equal(got["n"][ok[:, 0], 0], want["n"][ok[:, 0], 0])  # poisoned cells: exact once clean
     np.testing.assert_array_equal(got["n"][ok[:, 1], 1], want["n"][ok[:, 1], 1])
+
+
+@pytest.mark.parametrize("name", ["cats288", "cfgspace", "south_dt3"])
+def test_column_term_path_matches_oracle(name, cuda_device):
+    """The oracle, through the column-term pass (TFG_OPT_COLUMN_TERMS): every golden cell is replicated `rep` times behind
+    a forcing map, so that the forcing-only part of update() is evaluated once per column by column_terms_kernel and the
+    melt kernel runs its `PRE` instantiation.  All recorded quantities and integrals of every replica must meet the same
+    tolerances as the per-cell path (SURVEY.md section 8a table in helpers.ATOL)."""
+    import torch
+
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+
+    case, want = oracle_series(name)
+    n, T = case["N"], case["forcing"].shape[0]
+    rep = max(8, -(-65536 // (min(T, 128) * n)))          # >= 65 536 cell-steps per launch, >= 8 cells per column
+    statics = {k: np.repeat(np.asarray(v), rep) for k, v in case["statics"].items()}
+    col = np.repeat(np.arange(n, dtype=np.int32), rep)
+    consts = default_constants()
+    consts.update(case.get("consts", {}))
+    eng = MeltEngine(statics, consts, case["start_time"], dt_hours=case.get("dt", 1), zones=[case.get("tz", "America/Los_Angeles")],
+                     mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=n)
+    got = eng.run(torch.as_tensor(case["forcing"]).to(cuda_device), record=REC)
+    torch.cuda.synchronize()
+    assert eng.column_term_launches >= 1
+    got = {k: v.cpu().numpy() for k, v in got.items()}
+    got.update({k: eng.row(k).cpu().numpy() for k in VOLS})
+    bad = []
+    for k in REC + VOLS:
+        g = got[k].reshape(*got[k].shape[:-1], n, rep)
+        assert (g == g[..., :1]).all() or np.isnan(g).any(), k          # replicas of a cell agree bit for bit
+        ok, ratio, dabs, drel = err_report(g[..., 0], want[k], ATOL[k])
+        if not ok:
+            bad.append((k, ratio, dabs, drel))
+    eng.close()
+    assert not bad, bad
