@@ -26,6 +26,9 @@ static __constant__ LitTable kLit = {0.1636661211129296, 0.1636098885816659, 6.1
 #ifndef TFG_ALBEDO_EARLY  // fast float64 step: the albedo-ageing exponential (:1042-1048) is evaluated beside the W_p / e_sat(T_surf)
 #define TFG_ALBEDO_EARLY 1 // exponentials (one group of three shares table index arithmetic and coefficients); bit-identical, +0.7 %
 #endif
+#ifndef TFG_CT_HOIST   // column-term step: the late terms (W_p, e_sat(T_dew); LW_in, T_wb) are requested a section ahead of their use
+#define TFG_CT_HOIST 1
+#endif
 #ifndef TFG_EXP5   // experiment: all five exponentials of the met block in one group
 #define TFG_EXP5 0
 #endif
@@ -606,6 +609,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // Column terms bound (see column_terms_eval): only what depends on the cell is left of the met block
     static_assert(TFG_ALBEDO_EARLY && TFG_FOLD_CONSTS, "the column-term step is written for the default fast step");
     rTK = R(pre.rTK); e_air = R(pre.e_air); RH = R(pre.RH); T_dew = R(pre.T_dew);
+    double2 late0 = make_double2(0.0, 0.0);   // W_p, e_sat(T_dew): consumed at the end of this block
+    if constexpr (TFG_CT_HOIST) late0 = __ldg(reinterpret_cast<const double2*>(pre.line + kCtWp));
     const double lx1[1] = {nmax((R(k.z) - h_snow) * R(k.inv_z0), LIT(c001, 0.01)).v};
     double ly1[1];
     fm::log_tab_n<1>(lx1, ly1);
@@ -635,9 +640,10 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     fm::exp_tab_n<2>(ex2, ey2);
     alb_exp = R(ey2[1]);
     const R inv_p0 = R(ey2[0]) * R(k.inv_p0c);
-    W_p = R(pre.get(kCtWp));
+    if constexpr (!TFG_CT_HOIST) late0 = make_double2(pre.get(kCtWp), pre.get(kCtEsDew));
+    W_p = R(late0.x);
     // e_sat(T_surf): T_surf is the dew point, or 0 degC over a melting surface, where exp(17.3 * 0 / 237.3) = 1 exactly
-    e_sat_surf = sel(cover && (T_dew > 0.0), LIT(esat10, 6.11) * R(1.0), R(pre.get(kCtEsDew)));
+    e_sat_surf = sel(cover && (T_dew > 0.0), LIT(esat10, 6.11) * R(1.0), R(late0.y));
     Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
     e_surf = RH * e_sat_surf;                                                                // :853
     Qe = (Dh * fnmadd(RH, e_sat_surf, e_air)) * (R(ey2[0]) * R(k.cq0));                      // :931-934
@@ -761,6 +767,8 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);
   }
   mid_step();
+  double2 late1 = make_double2(0.0, 0.0);     // column terms LW_in, T_wb: consumed further down
+  if constexpr (Pre::on && TFG_CT_HOIST) late1 = __ldg(reinterpret_cast<const double2*>(pre.line + kCtLWin));
   // ---- update_julian_day :990-1004 ; True_Solar_Noon solar_funcs.py:1471
   const R solar_noon = (LIT(c12, 12.0) + LC) + R(tr.TE);
   const R th = R(tr.clock_hour) - solar_noon;
@@ -806,7 +814,9 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
   // ---- update_net_longwave_radiation :1231-1248
   const R T_surf_K = T_surf + LIT(kelvin, 273.15);
   R LW_in;
-  if constexpr (Pre::on) LW_in = R(pre.get(kCtLWin)); else LW_in = (em_air * R(k.sigma)) * npow4(T_K);
+  if constexpr (Pre::on && TFG_CT_HOIST) LW_in = R(late1.x);
+  else if constexpr (Pre::on) LW_in = R(pre.get(kCtLWin));
+  else LW_in = (em_air * R(k.sigma)) * npow4(T_K);
   R LW_out = R(k.es_sigma) * npow4(T_surf_K);
   LW_out = fmadd(R(k.one_m_es), LW_in, LW_out);
   const R Qn_LW = LW_in - LW_out;
@@ -840,7 +850,7 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     if constexpr (P::lean && TFG_WETBULB_TABLE) stull_fast = (RH >= 0.046875) && (RH <= 2.0);   // table bins 1..32
     else if constexpr (P::lean || P::f32) stull_fast = (RH >= 0.0) && (RH <= 2.0);
     if constexpr (Pre::on) {
-      T_wb = R(pre.get(kCtTwb));
+      if constexpr (TFG_CT_HOIST) T_wb = R(late1.y); else T_wb = R(pre.get(kCtTwb));
     } else if (stull_fast) {
       if constexpr (P::f32) T_wb = R(fm::stull_wet_bulb32(T_air.v, RH.v));
       else if constexpr (TFG_WETBULB_TABLE) T_wb = R(fm::stull_wet_bulb_tab(T_air.v, RH.v));
