@@ -18,6 +18,9 @@ ap.add_argument("--mode", default="f64_fast")
 ap.add_argument("--cells", type=int, default=4096 * 4096)
 ap.add_argument("--steps", type=int, default=8760)
 ap.add_argument("--chunk", type=int, default=128)
+ap.add_argument("--columns", type=int, default=0,
+                help="> 0: catchment forcing -- that many forcing series shared by consecutive cells (tfg_bind_forcing_map; the "
+                     "fast float64 mode then evaluates the forcing-only terms once per column, TFG_OPT_COLUMN_TERMS)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 NB = 4096
@@ -28,6 +31,11 @@ eng = MeltEngine(None, default_constants(), "2012100100", zones=[-8.0], mode=a.m
                  device_statics=tabs, basin_id=basin, n_basin=NB)
 elev = elev.to(eng.dtype)
 forcing = torch.empty(a.chunk, 5, a.cells, dtype=eng.dtype, device=dev)
+fcol = None
+if a.columns > 0:   # the series of the first `columns` cells serve as the catchments' met series
+    per = -(-a.cells // a.columns)
+    eng.set_forcing_map((torch.arange(a.cells, device=dev) // per).to(torch.int32), a.columns)
+    fcol = torch.empty(a.chunk, 5, a.columns, dtype=eng.dtype, device=dev)
 agg = BasinAggregates(a.chunk, NB, device=dev, exponents=eng.agg_exponents())
 runoff = torch.zeros(NB, dtype=torch.float64, device=dev)   # m3 per basin over the year
 rates, t_wall = [], time.perf_counter()
@@ -36,7 +44,9 @@ for t0 in range(0, a.steps, a.chunk):
     eng.synth_forcing(forcing, t0, n, elev, seed=20121001)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tgt = agg.zero()
-    s.record(); eng.run(forcing, n, basin_agg=tgt); e.record()
+    if fcol is not None:
+        fcol[:n].copy_(forcing[:n, :, :a.columns])
+    s.record(); eng.run(forcing if fcol is None else fcol, n, basin_agg=tgt); e.record()
     agg.reduce()
     runoff += agg.buffer[:n, :, 0].sum(dim=0) * 3600.0
     torch.cuda.synchronize()
@@ -44,7 +54,9 @@ for t0 in range(0, a.steps, a.chunk):
 wall = time.perf_counter() - t_wall
 kernel_s = sum(a.cells * min(a.chunk, a.steps - t0) / r for t0, r in zip(range(0, a.steps, a.chunk), rates))
 print(json.dumps({
-    "workload": f"{a.cells} cells x {a.steps} hourly steps, mode {a.mode}", "launches": len(rates),
+    "workload": f"{a.cells} cells x {a.steps} hourly steps, mode {a.mode}"
+                + (f", {a.columns} shared forcing columns (column terms: {eng.column_term_launches} launches)" if a.columns else ""),
+    "launches": len(rates),
     "cell_steps_per_s_year_mean": a.cells * a.steps / kernel_s, "kernel_seconds": kernel_s, "wall_seconds_incl_forcing_synthesis": wall,
     "chunk_rate_min": min(rates), "chunk_rate_max": max(rates),
     "chunk_rates_G": [round(r / 1e9, 2) for r in rates],
