@@ -137,7 +137,7 @@ TFG_API int tfg_mode(const tfg_ctx* ctx);
  * an integer all-reduce of the accumulators is exact.  Contributions that are not finite or exceed 2^E_q are left
  * out and counted in the trailing word.                                                                        */
 #define TFG_OPT_EXACT_AGG 2
-/* TFG_OPT_COLUMN_TERMS (default 1; TFG_F64_FAST contexts with a forcing map of at most n_cells / 8 columns): the part of
+/* TFG_OPT_COLUMN_TERMS (default 1; TFG_F64_FAST and TFG_F64_STRICT contexts with a forcing map of at most n_cells / 8 columns): the part of
  * update() that reads nothing but the forcings (vapour pressures, relative humidity, dew point, precipitable water,
  * air emissivity, incoming longwave, snowfall wet bulb: bmi_topoflow_glacier.py:423-425, :784-893, :919-920,
  * :1167-1234, :1507-1520) is evaluated once per forcing COLUMN and timestep by a small pass in front of each launch and

@@ -762,8 +762,9 @@ def test_netcdf_file_to_packed_streamer_to_kernel(tmp_path, cuda_device):
     eng.close()
 
 
-def test_column_terms_pass_is_bit_identical_and_taken(cuda_device):
-    """TFG_OPT_COLUMN_TERMS: with a forcing map of few columns the fast float64 engine evaluates the forcing-only part
+@pytest.mark.parametrize("mode", ["f64_fast", "f64"])
+def test_column_terms_pass_is_bit_identical_and_taken(mode, cuda_device):
+    """TFG_OPT_COLUMN_TERMS: with a forcing map of few columns a float64 engine (fast or strict) evaluates the forcing-only part
     of update() once per column and timestep (column_terms_kernel) -- every recorded quantity, the state, the snowfall
     window, the diagnostic integrals and the exact basin sums must equal the per-cell evaluation bit for bit, also where
     a column holds missing or absurd forcing (those cell-steps take the strict step from the raw values in both)."""
@@ -787,7 +788,7 @@ def test_column_terms_pass_is_bit_identical_and_taken(cuda_device):
     col = (np.arange(N) * M // N).astype(np.int32)                 # contiguous catchments ...
     col[::7] = np.random.default_rng(5).integers(0, M, col[::7].size)   # ... with foreign cells inside the warps
     basin = (np.arange(N) // 100).astype(np.int32)
-    kw = dict(zones=[-8.0], mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M,
+    kw = dict(zones=[-8.0], mode=mode, horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M,
               basin_id=basin, n_basin=30)
     f = torch.as_tensor(fcols).to(cuda_device, torch.float64).contiguous()
     out = {}
@@ -810,7 +811,8 @@ def test_column_terms_pass_is_bit_identical_and_taken(cuda_device):
     assert torch.isnan(out[True][1]).any()                         # the missing value did poison its cells
 
 
-def test_column_terms_on_the_per_step_path(cuda_device):
+@pytest.mark.parametrize("mode", ["f64_fast", "f64"])
+def test_column_terms_on_the_per_step_path(mode, cuda_device):
     """The literal update() (one-step launches, exact window re-sum) with the column-term pass in front: same state as
     without it, and as the fused launch, bit for bit (large enough for the pass to be taken: >= 65536 cell-steps)."""
     import torch
@@ -823,7 +825,7 @@ def test_column_terms_on_the_per_step_path(cuda_device):
     statics, _ = bench.synthetic_host_sample(N, 1, seed=21)
     _, fcols = bench.synthetic_host_sample(M, T, seed=22)
     col = (np.arange(N) % M).astype(np.int32)
-    kw = dict(zones=[-8.0], mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M)
+    kw = dict(zones=[-8.0], mode=mode, horizon_steps=T + 1, forcing_index=col, n_forcing_cols=M)
     f = torch.as_tensor(np.ascontiguousarray(fcols)).to(cuda_device, torch.float64).contiguous()
     states = []
     for on, fused in ((True, False), (False, False), (True, True)):

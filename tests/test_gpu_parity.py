@@ -465,8 +465,9 @@ def test_window_sum_recovers_from_missing_precipitation(mode, chunk, cuda_device
     np.testing.assert_array_equal(got["n"][ok[:, 1], 1], want["n"][ok[:, 1], 1])
 
 
-@pytest.mark.parametrize("name", ["cats288", "cfgspace", "south_dt3"])
-def test_column_term_path_matches_oracle(name, cuda_device):
+@pytest.mark.parametrize("name,mode", [("cats288", "f64_fast"), ("cfgspace", "f64_fast"), ("south_dt3", "f64_fast"),
+                                       ("cats288", "f64"), ("cfgspace", "f64"), ("satterlund", "f64")])
+def test_column_term_path_matches_oracle(name, mode, cuda_device):
     """The oracle, through the column-term pass (TFG_OPT_COLUMN_TERMS): every golden cell is replicated `rep` times behind
     a forcing map, so that the forcing-only part of update() is evaluated once per column by column_terms_kernel and the
     melt kernel runs its `PRE` instantiation.  All recorded quantities and integrals of every replica must meet the same
@@ -484,7 +485,7 @@ def test_column_term_path_matches_oracle(name, cuda_device):
     consts = default_constants()
     consts.update(case.get("consts", {}))
     eng = MeltEngine(statics, consts, case["start_time"], dt_hours=case.get("dt", 1), zones=[case.get("tz", "America/Los_Angeles")],
-                     mode="f64_fast", horizon_steps=T + 1, forcing_index=col, n_forcing_cols=n)
+                     mode=mode, horizon_steps=T + 1, forcing_index=col, n_forcing_cols=n)
     got = eng.run(torch.as_tensor(case["forcing"]).to(cuda_device), record=REC)
     torch.cuda.synchronize()
     assert eng.column_term_launches >= 1

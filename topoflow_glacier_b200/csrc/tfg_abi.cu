@@ -426,32 +426,31 @@ int tfg_run(tfg_ctx* x, const void* forcing, int64_t step0, int32_t n_steps, voi
       e = tfg::launch_run_f32(make_params<float>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad), rec, agg, vol, s);
     } else {
       auto p = make_params<double>(x, f, step0 + t0, nt, r, record_mask, a, n_basin, agg_bad);
-      if (x->mode == TFG_F64_STRICT) {
-        e = tfg::launch_run_strict(p, rec, agg, vol, s);
-      } else {
-        // Forcing map with few columns per cell: the forcing-only part of the step is evaluated once per column and
-        // timestep (column_terms_kernel) and the melt kernel reads one line per step instead of redoing it per cell.
-        // Same device functions either way: results do not depend on this switch (test_column_terms_*).
-        const size_t need = (size_t)nt * (size_t)x->n_cols * tfg::kCtCount * sizeof(double);
-        // (not for launches so small that a second kernel launch costs more than it saves: per-step BMI updates of a few cells)
-        if (x->column_terms && x->forcing_col && !x->use_tma && !x->c.satterlund && x->n_cols * 8 <= x->n_cells &&
-            (int64_t)nt * x->n_cells >= 65536 && need <= (size_t(1) << 31)) {
-          if (x->col_terms_bytes < need) {   // grows to the largest launch seen; a failed allocation leaves the plain path
-            if (x->col_terms) cudaFree(x->col_terms);
-            x->col_terms = nullptr; x->col_terms_bytes = 0;
-            const size_t want = (size_t)std::min<int64_t>(tfg::kMaxLaunchSteps, std::max<int32_t>(nt, n_steps)) * (size_t)x->n_cols *
-                                tfg::kCtCount * sizeof(double);
-            if (cudaMalloc(&x->col_terms, want) == cudaSuccess) x->col_terms_bytes = want;
-            else (void)cudaGetLastError();
-          }
-          if (x->col_terms_bytes >= need) {
-            e = tfg::launch_column_terms_fast(static_cast<const double*>(f), x->col_terms, nt, x->n_cols, p.k, s);
-            p.col_terms = x->col_terms;
-            ++x->col_term_launches;
-          }
+      const bool strict = x->mode == TFG_F64_STRICT;
+      // Forcing map with few columns per cell: the forcing-only part of the step is evaluated once per column and
+      // timestep (column_terms_kernel, in the arithmetic of the context's mode) and the melt kernel reads one line per
+      // step instead of redoing it per cell.  Same device functions either way: results do not depend on this switch
+      // (test_column_terms_*).  Not for launches so small that a second kernel launch costs more than it saves
+      // (per-step BMI updates of a few cells); the fast mode leaves SATTERLUND configurations to its strict step.
+      const size_t need = (size_t)nt * (size_t)x->n_cols * tfg::kCtCount * sizeof(double);
+      if (x->column_terms && x->forcing_col && !x->use_tma && (strict || !x->c.satterlund) && x->n_cols * 8 <= x->n_cells &&
+          (int64_t)nt * x->n_cells >= 65536 && need <= (size_t(1) << 31)) {
+        if (x->col_terms_bytes < need) {   // grows to the largest launch seen; a failed allocation leaves the plain path
+          if (x->col_terms) cudaFree(x->col_terms);
+          x->col_terms = nullptr; x->col_terms_bytes = 0;
+          const size_t want = (size_t)std::min<int64_t>(tfg::kMaxLaunchSteps, std::max<int32_t>(nt, n_steps)) * (size_t)x->n_cols *
+                              tfg::kCtCount * sizeof(double);
+          if (cudaMalloc(&x->col_terms, want) == cudaSuccess) x->col_terms_bytes = want;
+          else (void)cudaGetLastError();
         }
-        if (e == cudaSuccess) e = tfg::launch_run_fast(p, rec, agg, vol, s);
+        if (x->col_terms_bytes >= need) {
+          e = strict ? tfg::launch_column_terms_strict(static_cast<const double*>(f), x->col_terms, nt, x->n_cols, p.k, s)
+                     : tfg::launch_column_terms_fast(static_cast<const double*>(f), x->col_terms, nt, x->n_cols, p.k, s);
+          p.col_terms = x->col_terms;
+          ++x->col_term_launches;
+        }
       }
+      if (e == cudaSuccess) e = strict ? tfg::launch_run_strict(p, rec, agg, vol, s) : tfg::launch_run_fast(p, rec, agg, vol, s);
     }
   }
   if (e != cudaSuccess) return fail("tfg_run: kernel launch", e);

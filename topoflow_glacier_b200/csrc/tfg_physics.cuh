@@ -560,6 +560,49 @@ __device__ __forceinline__ void column_terms_eval(const Consts<double>& k, doubl
   for (int i = 0; i < kCtCount; i += 2) *reinterpret_cast<double2*>(out + i) = make_double2(o[i], o[i + 1]);
 }
 
+// The same terms in the strict arithmetic (libdevice functions, IEEE division, NumPy's NaN rules: the expressions of the
+// strict per-cell step, operation for operation), SATTERLUND configurations included.  There is no "sane" test in this
+// mode -- a missing value poisons the column's terms exactly as it poisons every cell of the column in the per-cell
+// step.  Slot kCtRTK carries e_sat(0 degC) here (the strict step has no use for 1/T_K).
+template <class P>
+__device__ __forceinline__ void column_terms_eval_strict(const Consts<double>& k, double Pp, double T_air_, double P_air_,
+                                                         double q_, double uz, double* out) {
+  using R = Num<P>;
+  static_assert(P::strict, "strict float64 mode");
+  const R T_air(T_air_), P_air(P_air_), q(q_);
+  const R T_K = T_air + LIT(kelvin, 273.15);
+  const R e_sat_air = e_sat_mbar<P>(k, T_air);
+  const R e = (q * P_air) / (R(k.eps) + (R(k.one_m_eps) * q));     // :817
+  const R e_air = (e / 1000.0) * 10.0;
+  const R RH = e_air / e_sat_air;                                  // :838
+  const R log_term = nlog(divk(e_air, 6.1121));                    // :888-893
+  const R T_dew = (LIT(dew_c, 257.14) * log_term) / (LIT(dew_b, 18.678) - log_term);
+  const R W_p = LIT(wp_a, 1.12) * nexp(LIT(wp_b, 0.0614) * T_dew);  // :919-920
+  double zero = 0.0;
+  asm volatile("" : "+d"(zero));   // opaque: e_sat(0) goes through the device functions like the per-cell step's, not the compiler's folding
+  const R es_dew = e_sat_mbar<P>(k, T_dew), es_zero = e_sat_mbar<P>(k, R(zero));
+  R em_air;                                                        // :1167-1192
+  if (!k.satterlund) {
+    const R x = divk(e_air, 10.0) / T_K;
+    const R term1 = R(k.emis_a) * npow(x, R(k.one_seventh));
+    em_air = fmadd(term1, R(k.emis_b), R(k.canopy));
+  } else {
+    em_air = R(1.08) * (R(1.0) - nexp(R(-1.0) * npow(e_air, divk(T_K, 2016.0))));
+  }
+  const R LW_in = (em_air * R(k.sigma)) * npow4(T_K);              // :1234
+  const R T_wb = ((((T_air * natan(LIT(st_a, 0.151977) * nsqrt(RH + LIT(st_b, 8.313659)))) + natan(T_air + RH)) -
+                   natan(RH - LIT(st_c, 1.676331))) +
+                  ((LIT(st_d, 0.00391838) * npow15(RH)) * natan(LIT(st_e, 0.023101) * RH))) -
+                 LIT(st_f, 4.86035);                                // :1507-1520
+  double o[kCtCount];
+  o[kCtP] = Pp; o[kCtTair] = T_air_; o[kCtUz] = uz; o[kCtPair] = P_air_; o[kCtQ] = q_;
+  o[kCtRTK] = es_zero.v; o[kCtEair] = e_air.v; o[kCtRH] = RH.v; o[kCtTdew] = T_dew.v; o[kCtSane] = 1.0;
+  o[kCtWp] = W_p.v; o[kCtEsDew] = es_dew.v; o[kCtLWin] = LW_in.v; o[kCtTwb] = T_wb.v; o[kCtEmAir] = em_air.v;
+  o[kCtEsatAir] = e_sat_air.v;
+#pragma unroll
+  for (int i = 0; i < kCtCount; i += 2) *reinterpret_cast<double2*>(out + i) = make_double2(o[i], o[i + 1]);
+}
+
 // One update().  `window_sum(ring_new)` must return the 72-slot snowfall-window sum AFTER this step's
 // entry `ring_new` replaced the oldest one (:1027-1037); the caller owns the window storage.
 // `mid_step()` is called once the pressure / humidity / wind forcings are dead (after the turbulent fluxes): the
@@ -728,6 +771,31 @@ __device__ __forceinline__ void cell_step(const Consts<typename P::raw>& k, cons
     // only read when a caller records them (dead code otherwise)
     p0 = R(1.0) / inv_p0; Ri = top / bot; Dn = uk2 / LL;
     e_sat_air = LIT(esat10, 6.11) / en;
+  } else if constexpr (Pre::on) {
+    // Strict step with the column terms bound (column_terms_eval_strict): the per-cell remainder, same operations
+    static_assert(P::strict, "column terms: float64 modes");
+    p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));                        // :551-556
+    p0 = (p0 / 1000.0) * 10.0;
+    e_sat_air = R(pre.get(kCtEsatAir)); e_air = R(pre.e_air); RH = R(pre.RH); T_dew = R(pre.T_dew);
+    const bool cover = (h_snow > 0.0) || (h_ice > 0.0);
+    T_surf = sel(cover, nmin(T_dew, R(0.0)), T_dew);                                         // :906-911
+    // e_sat(T_surf), :784-802: T_surf is the dew point or, over a melting surface with a dew point above freezing, 0 degC
+    e_sat_surf = sel(cover && (T_dew > 0.0), R(pre.rTK), R(pre.get(kCtEsDew)));
+    dT = T_air - T_surf;
+    const R top = R(k.gz) * dT;                                                              // :640-644
+    R bot = (uz * uz) * T_K;
+    bot = sel(bot == 0.0, R(0.01), bot);
+    Ri = top / bot;
+    const R zr = (R(k.z) - h_snow) / R(k.z0_air);                                            // :670-733
+    const R arg = R(k.kappa) / nlog(nmax(zr, R(0.01)));
+    Dn = uz * (arg * arg);
+    if (T_air == T_surf) Dh = Dn;
+    else if (Ri > 0.0) Dh = Dn / (R(1.0) + (R(10.0) * Ri));
+    else Dh = Dn * (R(1.0) - (R(10.0) * Ri));
+    Qh = (R(k.rho_cp_air) * Dh) * dT;                                                        // :744-745
+    W_p = R(pre.get(kCtWp));
+    e_surf = RH * e_sat_surf;                                                                // :853
+    Qe = ((R(k.rho_lv_air) * Dh) * (e_air - e_surf)) * (R(k.lhc) / p0);                      // :931-934
   } else {
     // ---- update_atm_pressure_from_elevation(T_C=True, MBAR=True) :551-556
     p0 = R(k.sea_p0) * nexp(R(s.get(kSaElev)) / (R(k.r_star) * T_K));

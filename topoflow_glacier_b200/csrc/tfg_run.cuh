@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
   }
 
   // forcing block [step][var][column]: column = cell, or the cell's entry of the forcing map
-  static_assert(!PRE || (P::lean && !TMA), "column terms: fast float64 mode, register prefetch");
+  static_assert(!PRE || (!P::f32 && !TMA), "column terms: float64 modes, no TMA staging");
   const int64_t FN = p.n_cols;
   // PRE: one line of kCtCount values per column and timestep instead of five forcing rows
   const raw* f = PRE ? p.col_terms + (int64_t)__ldg(p.forcing_col + c) * kCtCount
@@ -461,6 +461,9 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
         state_ok = finite(st.h_snow) && finite(st.h_swe) && finite(st.h_ice) && finite(st.h_iwe) &&
                    finite(st.eccs) && finite(st.ecci) && finite(st.albedo) && finite(st.n_days);
       }
+    } else if constexpr (PRE) {   // strict float64 with column terms (no sanity test: NaN rules apply as they come)
+      const ColumnTerms pre{f2, f3, e0, e1, f + (int64_t)t * (kCtCount * FN)};
+      cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(0.0), R(0.0), R(f4), window, prefetch, o, pre);
     } else {
       cell_step<P, VOL>(p.k, row, s, LC, st, R(f0), R(f1), R(f2), R(f3), R(f4), window, prefetch, o);
     }
@@ -567,22 +570,25 @@ __global__ void __launch_bounds__(kBlock, P::lean ? TFG_MIN_BLOCKS_LEAN : (P::f3
 template <class P>
 __global__ void __launch_bounds__(256) column_terms_kernel(const double* __restrict__ forcing, double* __restrict__ out,
                                                            int32_t n_steps, int64_t n_cols, const Consts<double> k) {
-  for (int i = threadIdx.x; i < fm::kTabDoubles; i += blockDim.x)
-    fm::tfg_tabs[i] = (i < 64) ? fm::kExpTab[i] : fm::kLogTab[(i - 64) >> 1][(i - 64) & 1];
-  __syncthreads();
+  if constexpr (P::lean) {
+    for (int i = threadIdx.x; i < fm::kTabDoubles; i += blockDim.x)
+      fm::tfg_tabs[i] = (i < 64) ? fm::kExpTab[i] : fm::kLogTab[(i - 64) >> 1][(i - 64) & 1];
+    __syncthreads();
+  }
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_steps * n_cols) return;
   const int64_t t = idx / n_cols, col = idx - t * n_cols;
   const double* f = forcing + t * (TFG_N_FORCING * n_cols) + col;
   const double f0 = f[0], f1 = f[n_cols], f2 = f[2 * n_cols], f3 = f[3 * n_cols], f4 = f[4 * n_cols];
-  column_terms_eval<P>(k, f0, f1, f2, f3, f4, forcings_sane(f0, f1, f2, f3, f4), out + idx * kCtCount);
+  if constexpr (P::lean) column_terms_eval<P>(k, f0, f1, f2, f3, f4, forcings_sane(f0, f1, f2, f3, f4), out + idx * kCtCount);
+  else column_terms_eval_strict<P>(k, f0, f1, f2, f3, f4, out + idx * kCtCount);
 }
 
 template <class P>
 cudaError_t launch_column_terms(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
                                 cudaStream_t stream) {
   const int64_t total = (int64_t)n_steps * n_cols;
-  column_terms_kernel<P><<<(unsigned)((total + 255) / 256), 256, fm::kTabDoubles * sizeof(double), stream>>>(forcing, out, n_steps,
+  column_terms_kernel<P><<<(unsigned)((total + 255) / 256), 256, P::lean ? fm::kTabDoubles * sizeof(double) : 0, stream>>>(forcing, out, n_steps,
                                                                                                            n_cols, k);
   return cudaGetLastError();
 }
@@ -595,7 +601,7 @@ cudaError_t launch_run(const RunParams<typename P::raw>& p, bool rec, bool agg, 
                    ((reinterpret_cast<uintptr_t>(p.forcing) & 15) == 0) &&
                    ((p.n_cells * sizeof(typename P::raw)) % 16 == 0);
   const size_t dyn = P::lean ? fm::kTabDoubles * sizeof(double) : 0;
-  if constexpr (P::lean) {
+  if constexpr (!P::f32) {
     if (p.col_terms != nullptr) {  // column terms bound (forcing map): the kernel reads them instead of the forcing block
       if (rec) run_kernel<P, true, true, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
       else if (agg && vol) run_kernel<P, false, true, true, false, true><<<grid, kBlock, dyn, stream>>>(p);
@@ -624,5 +630,7 @@ cudaError_t launch_run_fast(const RunParams<double>& p, bool rec, bool agg, bool
 cudaError_t launch_run_f32(const RunParams<float>& p, bool rec, bool agg, bool vol, cudaStream_t stream);
 cudaError_t launch_column_terms_fast(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
                                      cudaStream_t stream);
+cudaError_t launch_column_terms_strict(const double* forcing, double* out, int32_t n_steps, int64_t n_cols, const Consts<double>& k,
+                                       cudaStream_t stream);
 
 }  // namespace tfg
