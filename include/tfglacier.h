@@ -193,6 +193,13 @@ TFG_API int tfg_run(tfg_ctx* ctx, const void* forcing, int64_t step0, int32_t n_
  * (cudaEvent_t as void*, may be NULL).                                                          */
 TFG_API int tfg_ingest_async(tfg_ctx* ctx, const void* pinned_src, void* dev_dst, size_t bytes, void* stream,
                      void* done_event);
+/* Page-locked host staging memory for the sources of tfg_ingest_async (cudaHostAlloc; no context needed).  With
+ * write_combined != 0 the block is write-combined: host writes stream past the CPU caches and the device's reads over
+ * PCIe need no cache snoop -- meant for buffers the host only fills (host READS of such memory are slow).           */
+TFG_API int tfg_host_alloc(void** out, size_t bytes, int write_combined);
+TFG_API int tfg_host_free(void* block);
+/* 1 if `p` points into page-locked host memory (cudaHostAlloc / cudaHostRegister, whoever allocated it), else 0 */
+TFG_API int tfg_host_is_pinned(const void* p);
 /* raw met columns -> live forcings, on the device:
  *   raw dev [n_steps][6][n_cells] float64 (raw_elem_size 8) or float32 (4; widened exactly, e.g. AORC/NWM
  *       single-precision sources): RAINRATE [mm/h], T2D [K], PSFC [Pa], Q2D, U2D, V2D

@@ -842,3 +842,40 @@ def test_column_terms_on_the_per_step_path(mode, cuda_device):
         e.close()
     for s, r in states[1:]:
         assert torch.equal(states[0][0], s) and torch.equal(states[0][1], r)
+
+
+def test_write_combined_host_block_streams_like_a_pinned_one(cuda_device):
+    """forcing.pinned_block (tfg_host_alloc, write-combined pages): recognised as page-locked memory, taken by the
+    streamer without a staging copy, same device forcing and state as the NumPy source; freed with the tensor."""
+    import gc
+
+    import torch
+
+    import bench
+    from helpers import default_constants
+    from topoflow_glacier_b200.engine import MeltEngine
+    from topoflow_glacier_b200.forcing import ForcingStreamer, pack_forcing, pinned_block
+
+    N, T = 512, 12
+    statics, f = bench.synthetic_host_sample(N, T, seed=31)
+    raw = np.stack([f[:, 0] * 1e3, f[:, 1] + 273.15, f[:, 2], f[:, 3], f[:, 4] * 0.6, f[:, 4] * 0.8], axis=1)
+    packed = pack_forcing(raw)
+    blk = pinned_block(packed.shape, torch.int16)
+    from topoflow_glacier_b200 import _lib
+
+    assert _lib.load().tfg_host_is_pinned(blk.data_ptr()) == 1 and blk.dtype == torch.int16 and tuple(blk.shape) == packed.shape
+    assert _lib.load().tfg_host_is_pinned(packed.ctypes.data) == 0
+    blk.copy_(torch.as_tensor(packed))
+    states = []
+    for src in (blk, packed):
+        e = MeltEngine(statics, default_constants(), "2013020100", zones=[-8.0], mode="f64_fast", horizon_steps=T + 1)
+        s = ForcingStreamer(e, chunk_steps=5, raw_dtype="int16")
+        s.drive(src)
+        torch.cuda.synchronize()
+        if src is blk:
+            assert all(p is None for p in s.pinned)            # no staging copy: the block is DMA-ed from where it lies
+        states.append(e.state.clone())
+        e.close()
+    assert torch.equal(states[0], states[1])
+    del blk
+    gc.collect()

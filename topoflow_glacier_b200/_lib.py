@@ -64,6 +64,9 @@ PROTOTYPES = {
     "tfg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "tfg_destroy": (None, [C.c_void_p]),
     "tfg_mode": (C.c_int, [C.c_void_p]),
+    "tfg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "tfg_host_free": (C.c_int, [C.c_void_p]),
+    "tfg_host_is_pinned": (C.c_int, [C.c_void_p]),
     "tfg_column_term_launches": (C.c_int64, [C.c_void_p]),
     "tfg_elem_size": (C.c_size_t, [C.c_void_p]),
     "tfg_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),

@@ -466,6 +466,23 @@ int tfg_ingest_async(tfg_ctx* x, const void* pinned_src, void* dev_dst, size_t b
   return 0;
 }
 
+int tfg_host_alloc(void** out, size_t bytes, int write_combined) {
+  if (!out || bytes == 0) return fail("tfg_host_alloc: bad argument");
+  TFG_CUDA(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return 0;
+}
+
+int tfg_host_free(void* block) {
+  if (block) TFG_CUDA(cudaFreeHost(block));
+  return 0;
+}
+
+int tfg_host_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int tfg_stream_wait_event(tfg_ctx* x, void* stream, void* event) {
   if (!x || !event) return fail("tfg_stream_wait_event: NULL argument");
   TFG_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0));

@@ -152,6 +152,30 @@ def write_forcing_netcdf(path, when: pd.DatetimeIndex, raw: np.ndarray, packing=
             v[:] = packed[:, j, :]
 
 
+def pinned_block(shape, dtype, write_combined: bool = True):
+    """A page-locked host tensor for ``ForcingStreamer`` sources (``tfg_host_alloc``).  ``write_combined`` (default)
+    asks for write-combined pages: the host only FILLS such a block (reads from it are slow), and the device's reads
+    over PCIe then need no cache snoop.  The memory is released when the tensor is garbage-collected."""
+    import ctypes as C
+    import weakref
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    dtype = {np.dtype("int16"): torch.int16, np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}.get(
+        np.dtype(dtype) if not isinstance(dtype, torch.dtype) else None, dtype)
+    n = int(np.prod(shape))
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    ptr = C.c_void_p()
+    _lib.check(lib.tfg_host_alloc(C.byref(ptr), nbytes, int(bool(write_combined))), "tfg_host_alloc")
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    t = torch.frombuffer(buf, dtype=dtype, count=n).view(*shape)
+    weakref.finalize(buf, lib.tfg_host_free, C.c_void_p(ptr.value))   # the tensor keeps `buf` alive
+    return t
+
+
 def bind_host_to_gpu(device_index: int) -> bool:
     """Pin the calling process to the CPU cores next to GPU ``device_index`` (NVML's ideal affinity), so that pinned
     staging buffers allocated afterwards are first-touched on that GPU's NUMA node.  With several ranks streaming
@@ -213,7 +237,10 @@ class ForcingStreamer:
         """
         torch, lib, e = self.torch, self.e.lib, self.e
         Tk = block.shape[0]
-        if torch.is_tensor(block) and block.is_pinned() and block.is_contiguous() and block.dtype == self.raw_dtype:
+        # page-locked sources are copied from where they lie (torch's own pinned tensors, or any cudaHostAlloc'ed block such
+        # as forcing.pinned_block: torch only recognises the former, the library asks the driver)
+        if (torch.is_tensor(block) and block.device.type == "cpu" and block.is_contiguous() and block.dtype == self.raw_dtype
+                and (block.is_pinned() or lib.tfg_host_is_pinned(block.data_ptr()) == 1)):
             src_ptr = block.data_ptr()
             self._keepalive = block
         else:
