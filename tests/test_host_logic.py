@@ -307,3 +307,22 @@ def test_hydrofabric_shipped_gpkg_matches_configs():
         assert h.area_of([name])[0] == cfg["da"]
     b, names = h.basin_ids(h.divide_id)
     assert set(b) == {0} and len(names) == 1
+
+
+def test_pinned_block_needs_the_cuda_library():
+    """forcing.pinned_block allocates through the C ABI (cudaHostAlloc): without a GPU it fails loudly instead of handing
+    out pageable memory; tfg_host_is_pinned answers 0 for ordinary host memory."""
+    import torch
+
+    from topoflow_glacier_b200 import _lib
+    from topoflow_glacier_b200.forcing import pinned_block
+
+    lib = _lib.load()
+    a = np.zeros(16)
+    assert lib.tfg_host_is_pinned(a.ctypes.data) == 0 and lib.tfg_host_is_pinned(None) == 0
+    if torch.cuda.is_available():
+        blk = pinned_block((4, 6, 8), torch.int16)
+        assert lib.tfg_host_is_pinned(blk.data_ptr()) == 1
+    else:
+        with pytest.raises(RuntimeError, match="tfg_host_alloc"):
+            pinned_block((4, 6, 8), torch.int16)
